@@ -1,0 +1,124 @@
+/*
+ * Batched / B200-specific C ABI of libqpswift_b200.so (plain pointers and sizes only).
+ *
+ * The reference has no batched entry point; BASELINE.json's north_star names QP_SOLVE_BATCH as
+ * the new export next to the unchanged QP_SETUP / QP_SOLVE / QP_CLEANUP (qpSWIFT/qpSWIFT.h).
+ * Everything here is what a cgo / ctypes / C++ caller binds; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - "value row" of one QP = the nonzero values of P, A, G in the CCS order of the prototype's
+ *     pattern (exactly what QP_SETUP receives as Ppr/Apr/Gpr), plus c[n], h[m], b[p].
+ *   - batch arrays are row-per-QP, C contiguous: Ppr[batch][nnzP], ..., x[batch][n], ...
+ *   - return values < 0 are QPB_E_* errors (CUDA failures are never silent, and there is no
+ *     CPU fallback: without a usable device every compute call returns QPB_E_NODEVICE).
+ */
+#ifndef QPSWIFT_B200_H
+#define QPSWIFT_B200_H
+
+#include "qpSWIFT/qpSWIFT.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QPB_E_NODEVICE (-101) /* no CUDA device / driver                        */
+#define QPB_E_CUDA (-102)     /* a CUDA call failed; see QPB_LAST_ERROR()       */
+#define QPB_E_ARG (-103)      /* bad argument (null pointer, count > capacity)  */
+#define QPB_E_PATTERN (-104)  /* unusable sparsity pattern (empty row of G)     */
+
+/* ---------------------------------------------------------------------------------------------
+ * Symbolic plan (host only, no GPU needed).  Replaces, once per sparsity pattern, what the
+ * reference recomputes per QP: formkktmatrix_full (src/qpSWIFT/Auxilary.c:71-181), amd_l_order
+ * (amd_order.c:21-199), LDL_symbolic (ldl.c:187-240) and the integer half of LDL_numeric
+ * (ldl.c:276-298,315).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct QPBPlan QPBPlan;
+
+/* A* may be NULL with p == 0; Permut may be NULL (AMD ordering). Never returns NULL. */
+QPBPlan *QPB_PLAN_CREATE(qp_int n, qp_int m, qp_int p, const qp_int *Pjc, const qp_int *Pir, const qp_int *Ajc, const qp_int *Air, const qp_int *Gjc, const qp_int *Gir, const qp_int *Permut);
+void QPB_PLAN_DESTROY(QPBPlan *plan);
+
+enum QPBPlanArray
+{
+	QPB_PLAN_KJC = 0, /* KKT column pointers [N+1]           */
+	QPB_PLAN_KIR = 1, /* KKT row indices [nnzK]              */
+	QPB_PLAN_P = 2,   /* permutation [N]                     */
+	QPB_PLAN_PINV = 3,
+	QPB_PLAN_PARENT = 4, /* elimination tree [N]             */
+	QPB_PLAN_LNZ = 5,    /* column counts of L [N]           */
+	QPB_PLAN_LP = 6,     /* column pointers of L [N+1]       */
+	QPB_PLAN_LI = 7      /* row indices of L [Lp[N]]         */
+};
+/* Pointer to a plan array (owned by the plan) and its length. */
+const qp_int *QPB_PLAN_ARRAY(const QPBPlan *plan, int which, qp_int *count);
+
+enum QPBPlanInfo
+{
+	QPB_INFO_N = 0, /* KKT dimension n+p+m */
+	QPB_INFO_NNZK = 1,
+	QPB_INFO_LNZ = 2,
+	QPB_INFO_AMD_STATUS = 3,
+	QPB_INFO_FACTOR_FLOPS = 4, /* sum Lnz_k (Lnz_k + 2), ldl.c:182-184 */
+	QPB_INFO_NNZU = 5,         /* upper-triangular KKT entries the factorisation reads */
+	QPB_INFO_VALID = 6,
+	QPB_INFO_PLAN_WORDS = 7 /* int32 words of the device plan */
+};
+qp_int QPB_PLAN_INFO(const QPBPlan *plan, int what);
+
+/* The ordering alone (test hook for amd_l_order, amd_order.c:21-199): returns the AMD status
+ * (0 ok, 1 ok-but-jumbled, -2 invalid) and writes Perm[n]. */
+qp_int QPB_AMD_ORDER(qp_int n, const qp_int *Ap, const qp_int *Ai, qp_int *Perm);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched solve.  One plan, `capacity` QPs resident on ONE device (the caller shards a larger
+ * batch across GPUs/processes: QPs are independent, see DESIGN.md "multi-GPU").
+ * ------------------------------------------------------------------------------------------- */
+typedef struct QPBatch QPBatch;
+
+/* proto supplies n, m, p, the CCS patterns of P, A, G, the permutation and sigma_d.  Settings
+ * are NOT captured: they are read from `proto->options` by every QP_SOLVE_BATCH call, like
+ * QP_SOLVE reads them at call time (qpSWIFT.c:502,521).  device < 0 -> current device. */
+QPBatch *QP_SETUP_BATCH(const QP *proto, qp_int capacity, int device);
+
+/* Same, from a bare plan plus settings (no QP struct needed; used by bindings). */
+QPBatch *QPB_BATCH_CREATE(const QPBPlan *plan, qp_real sigma_d, qp_int capacity, int device);
+
+/* Host-pointer solve (pageable or pinned).  Copies the value rows H2D, solves, copies results
+ * D2H.  Apr/b may be NULL when p == 0; any output pointer may be NULL.  Returns the number of
+ * QPs whose flag is not QP_OPTIMAL, or a negative QPB_E_* code.
+ * Per-QP semantics = QP_SETUP (initial point, Auxilary.c:992-1089) + QP_SOLVE (qpSWIFT.c:473-644). */
+qp_int QP_SOLVE_BATCH(QPBatch *batch, qp_int count, const settings *opts, const qp_real *Ppr, const qp_real *Apr, const qp_real *Gpr, const qp_real *c, const qp_real *h, const qp_real *b, qp_real *x, qp_real *y, qp_real *z, qp_real *s, qp_int *flag, qp_int *iters);
+
+/* Device-pointer solve on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ * Asynchronous: nothing is synchronised, the return value is 0 or a negative QPB_E_* code.
+ * flag/iters are int32 on the device; fval/stat (may be NULL) receive the objective value and
+ * [n_rx, n_ry, n_rz, n_mu, alpha_p, alpha_d, sigma, mu] per QP. */
+qp_int QP_SOLVE_BATCH_DEVICE(QPBatch *batch, qp_int count, const settings *opts, const qp_real *dPpr, const qp_real *dApr, const qp_real *dGpr, const qp_real *dc, const qp_real *dh, const qp_real *db, qp_real *dx, qp_real *dy, qp_real *dz, qp_real *ds, int *dflag, int *diters, qp_real *dfval, qp_real *dstat, void *stream);
+
+void QP_CLEANUP_BATCH(QPBatch *batch);
+
+/* Device time (ms, CUDA events) of the kernels of the last QP_SOLVE_BATCH call and the number
+ * of kernel launches it made. */
+double QPB_BATCH_LAST_KERNEL_MS(const QPBatch *batch);
+qp_int QPB_BATCH_LAST_LAUNCHES(const QPBatch *batch);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel-level entry points (device pointers), used by the parity tests to check each
+ * reference routine on its own and by bench.py to time the factor / solve kernels alone.
+ * ------------------------------------------------------------------------------------------- */
+
+/* LDL_numeric (ldl.c:253-326) for `count` QPs: vals[count][nV] value rows, zdiag[count][m]
+ * the (z,z) diagonal (e.g. -1 or -s/z); writes Lx[count][lnz], D[count][N]. */
+qp_int QPB_LDL_NUMERIC_BATCH(QPBatch *batch, qp_int count, const qp_real *dvals, const qp_real *dzdiag, qp_real *dLx, qp_real *dD, void *stream);
+
+/* LDL_perm, lsolve, dsolve, ltsolve, permt (ldl.c:495-597) for `count` QPs:
+ * rhs[count][N] -> sol[count][N] (may alias). */
+qp_int QPB_LDL_SOLVE_BATCH(QPBatch *batch, qp_int count, const qp_real *dLx, const qp_real *dD, const qp_real *drhs, qp_real *dsol, void *stream);
+
+const char *QPB_LAST_ERROR(void);
+int QPB_DEVICE_COUNT(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPSWIFT_B200_H */
