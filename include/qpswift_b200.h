@@ -99,6 +99,13 @@ void QP_CLEANUP_BATCH(QPBatch *batch);
 
 /* Device time (ms, CUDA events) of the kernels of the last QP_SOLVE_BATCH call and the number
  * of kernel launches it made. */
+/* fval[count] and stat[count][8] = {n_rx, n_ry, n_rz, n_mu, alpha_p, alpha_d, sigma, mu} of the last
+ * host-pointer QP_SOLVE_BATCH call (what QP_SOLVE stores into `stats`, qpSWIFT.c:507-596). */
+qp_int QPB_BATCH_READ_STATS(QPBatch *batch, qp_int count, qp_real *fval, qp_real *stat);
+
+/* sigma_d belongs to a QP, not to its pattern: change it between solves. */
+qp_int QPB_BATCH_SET_SIGMA_D(QPBatch *batch, qp_real sigma_d);
+
 double QPB_BATCH_LAST_KERNEL_MS(const QPBatch *batch);
 qp_int QPB_BATCH_LAST_LAUNCHES(const QPBatch *batch);
 
