@@ -131,7 +131,10 @@ def _plan_of(qp) -> dict:
 def solve_sparse(pat, Ppr, Apr, Gpr, c, h, b, *, kind=None, sigma_d=0.0, permut=None, maxit=None, reltol=None,
                  abstol=None, want_factor=False) -> Solution:
     """``QP_SETUP`` (CCS, shared pattern) + ``QP_SOLVE`` + ``QP_CLEANUP`` for ONE instance."""
-    lb = lib(kind or best_kind())
+    kind = kind or best_kind()
+    lb = lib(kind)
+    if kind == "port" and permut is None:
+        permut = golden_permutation(pat)  # the port does not restate AMD (see qpswift_port.c header)
     keep = [np.ascontiguousarray(a, dtype=np.int64) for a in (pat.Pjc, pat.Pir, pat.Ajc, pat.Air, pat.Gjc, pat.Gir)]
     vals = [np.ascontiguousarray(a, dtype=np.float64).copy() for a in (Ppr, Apr, Gpr, c, h, b)]
     perm = np.ascontiguousarray(permut, dtype=np.int64).copy() if permut is not None else None
@@ -170,6 +173,22 @@ def solve_sparse(pat, Ppr, Apr, Gpr, c, h, b, *, kind=None, sigma_d=0.0, permut=
     return sol
 
 
+_GOLDEN_PLANS = None
+
+
+def golden_permutation(pat):
+    """AMD permutation of a DogBot pattern from tests/golden/plans.npz (made by the real reference)."""
+    global _GOLDEN_PLANS
+    if _GOLDEN_PLANS is None:
+        _GOLDEN_PLANS = np.load(os.path.join(os.path.dirname(HERE), "tests", "golden", "plans.npz"))
+    key = f"{pat.kind}_P"
+    if key not in _GOLDEN_PLANS.files:
+        raise KeyError(f"no golden AMD permutation for pattern {pat.kind!r}: pass permut= or build oracle/_ref")
+    P = _GOLDEN_PLANS[key]
+    assert len(P) == pat.N
+    return P
+
+
 def solve_batch(batch, *, kind=None, **kw):
     """Loop of :func:`solve_sparse` over a ``dogbot.Batch``; returns stacked arrays."""
     sols = [solve_sparse(batch.pattern, batch.Ppr[i], batch.Apr[i], batch.Gpr[i], batch.c[i], batch.h[i], batch.b[i],
@@ -203,3 +222,52 @@ def fnv1a(a) -> str:
         h ^= v & 0xFFFFFFFFFFFFFFFF
         h = (h * 1099511628211) & 0xFFFFFFFFFFFFFFFF
     return f"{h:016x}"
+
+
+DRIVER_SO = os.path.join(HERE, "liboracle_driver.so")
+_DRIVER = None
+
+
+def run_batch(batch, *, kind=None, threads=None, permut="shared", sigma_d=0.0, maxit=None, reltol=None, abstol=None,
+              outputs=True):
+    """Whole batch through ``QP_SETUP`` + ``QP_SOLVE`` + ``QP_CLEANUP``, one instance per host thread
+    (oracle/ref_driver.c).  ``permut="shared"``: the pattern's AMD permutation is computed once and
+    supplied to every QP_SETUP (plan-reuse baseline); ``None``: every
+    instance runs AMD itself (only the real reference can); an array: that permutation.
+    Returns (result dict, wall seconds)."""
+    global _DRIVER
+    kind = kind or best_kind()
+    if _DRIVER is None:
+        if not os.path.exists(DRIVER_SO):
+            raise FileNotFoundError(f"{DRIVER_SO} missing: run `make -C oracle driver`")
+        _DRIVER = C.CDLL(DRIVER_SO, mode=C.RTLD_LOCAL)
+        _DRIVER.oracle_run_batch.restype = D
+    pat = batch.pattern
+    cnt = batch.count
+    if isinstance(permut, str):
+        if kind == "reference":
+            i0 = 0
+            permut = solve_sparse(pat, batch.Ppr[i0], batch.Apr[i0], batch.Gpr[i0], batch.c[i0], batch.h[i0], batch.b[i0],
+                                  kind="reference", maxit=0).plan["P"]
+        else:
+            permut = golden_permutation(pat)
+    if permut is None and kind == "port":
+        permut = golden_permutation(pat)
+    ints = [np.ascontiguousarray(a, dtype=np.int64) for a in (pat.Pjc, pat.Pir, pat.Ajc, pat.Air, pat.Gjc, pat.Gir)]
+    perm = np.ascontiguousarray(permut, dtype=np.int64) if permut is not None else None
+    vals = [np.ascontiguousarray(a, dtype=np.float64) for a in (batch.Ppr, batch.Apr, batch.Gpr, batch.c, batch.h, batch.b)]
+    out = {"x": np.empty((cnt, pat.n)), "y": np.empty((cnt, pat.p)), "z": np.empty((cnt, pat.m)), "s": np.empty((cnt, pat.m)),
+           "flag": np.empty(cnt, dtype=np.int64), "iters": np.empty(cnt, dtype=np.int64), "fval": np.empty(cnt)}
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None and a.size else None
+    path = (REF_SO if kind == "reference" else PORT_SO).encode()
+    threads = threads or (os.cpu_count() or 1)
+    secs = _DRIVER.oracle_run_batch(
+        C.c_char_p(path), C.c_int(int(threads)), C.c_long(cnt), L(pat.n), L(pat.m), L(pat.p),
+        *[vp(a) for a in ints], vp(perm), *[vp(a) for a in vals], D(float(sigma_d)),
+        L(-1 if maxit is None else int(maxit)), D(-1.0 if reltol is None else float(reltol)),
+        D(-1.0 if abstol is None else float(abstol)),
+        *([vp(out[k]) for k in ("x", "y", "z", "s", "flag", "iters", "fval")] if outputs else [None] * 7))
+    if secs < 0:
+        raise RuntimeError("oracle driver could not load " + path.decode())
+    out["threads"] = int(min(threads, max(cnt, 1)))
+    return out, float(secs)
