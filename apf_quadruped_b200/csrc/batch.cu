@@ -1,14 +1,20 @@
 // Kernels and host-side launch code of the batched solver; the C ABI of include/qpswift_b200.h.
 //
-// Launch shape: one warp per CTA, one QP per warp at a time, persistent CTAs that pull QP indices
-// from an atomic work counter (iteration counts differ per QP, so static striding would leave
-// SMs idle behind a slow instance).  Each warp keeps its QP's whole working set -- value row,
-// factor, iterate, residuals -- in its own slice of shared memory, so the interior-point loop
-// never touches HBM between the coalesced load of the value row and the store of the solution.
+// Launch shape: ONE persistent CTA per SM, one QP per warp, as many warps as slices of shared
+// memory fit (a slice = one QP's whole working set: value row, factor, scratch, iterate,
+// residuals; SliceLayout in program.h).  Between the coalesced load of its value row and the store
+// of its solution a QP never touches HBM.  The warps of a CTA walk the interior-point iteration in
+// lock step -- [residuals + stop test | factor | solve | step length, sigma | solve | update] --
+// so that they stream the same instruction words of the factor / solve schedules at the same time
+// (one L2 read per CTA, L1 hits for the other warps).  A warp whose QP has converged stores it and
+// pulls the next QP index from an atomic counter at the top of the cycle; the new QP's initial
+// point (kkt_initialize) is just another factor + solve in the same cycle, so iteration counts that
+// differ from QP to QP cost no idle cycles.
 
 #include "capi_internal.h"
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -36,109 +42,176 @@ static int fail(int code, const char *what, cudaError_t e)
 // kernels
 // ------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(32) qp_solve_fused_kernel(const int *__restrict__ plan, SmemLayout lay, BatchIO io, SolveParams prm, int *__restrict__ counter)
+struct ProgramView
+{
+	const uint2 *words;
+	int f_first, f_waves, s_first, s_waves;
+};
+
+enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_PRED = 2, MODE_CENT = 3 };
+static const int MAX_WARPS_PER_CTA = 16;
+
+__global__ void __launch_bounds__(MAX_WARPS_PER_CTA * 32, 1) qp_solve_cta_kernel(const int *__restrict__ plan, ProgramView pg, SliceLayout lay, BatchIO io, SolveParams prm, int *__restrict__ counter)
 {
 	extern __shared__ __align__(16) double smem[];
 	const PlanView pv = view_of(plan);
-	WarpState w = carve(smem, lay);
-	const int lane = lane_id();
+	const int lane = lane_id(), warp = threadIdx.x >> 5;
+	double *S = smem + (size_t)warp * lay.total;
+	WarpState w = carve(S, lay);
+	if (lane == 0) { S[lay.zero] = 0.0; S[lay.zero + 1] = -0.0; }
+	__syncwarp();
+	const int n = pv.n, m = pv.m, p = pv.p;
+	const double thr = prm.reltol / sqrt(3.0);
+
+	int q = 0, iters = 0;
+	bool active = false; // a QP is between its initial point and its exit
+	double sigma = 0.0, mu = 0.0, ap = 0.0, ad = 0.0;
+	Scalars sc;
+	sc.n_rx = sc.n_ry = sc.n_rz = sc.n_mu = sc.fval = 0.0;
+
 	for (;;) {
-		int q = 0;
-		if (lane == 0) q = atomicAdd(counter, 1);
-		q = __shfl_sync(0xffffffffu, q, 0);
-		if (q >= io.count) break;
-		const size_t qi = (size_t)q;
-		warp_copy_in(w.V, io.Ppr + qi * pv.offA, pv.offA);
-		if (pv.p) warp_copy_in(w.V + pv.offA, io.Apr + qi * (pv.offG - pv.offA), pv.offG - pv.offA);
-		warp_copy_in(w.V + pv.offG, io.Gpr + qi * (pv.nV - pv.offG), pv.nV - pv.offG);
-		warp_copy_in(w.c, io.c + qi * pv.n, pv.n);
-		warp_copy_in(w.h, io.h + qi * pv.m, pv.m);
-		if (pv.p) warp_copy_in(w.b, io.b + qi * pv.p, pv.p);
-		__syncwarp();
-
-		ipm_initial_point(pv, w);
-		const SolveResult res = ipm_solve(pv, w, prm);
-
-		warp_copy_out(io.x ? io.x + qi * pv.n : nullptr, w.x, pv.n);
-		if (pv.p) warp_copy_out(io.y ? io.y + qi * pv.p : nullptr, w.y, pv.p);
-		warp_copy_out(io.z ? io.z + qi * pv.m : nullptr, w.z, pv.m);
-		warp_copy_out(io.s ? io.s + qi * pv.m : nullptr, w.s, pv.m);
-		if (lane == 0) {
-			if (io.flag) io.flag[q] = res.flag;
-			if (io.iters) io.iters[q] = res.iters;
-			if (io.fval) io.fval[q] = res.sc.fval;
-			if (io.stat) {
-				double *st = io.stat + qi * 8;
-				st[0] = res.sc.n_rx; st[1] = res.sc.n_ry; st[2] = res.sc.n_rz; st[3] = res.sc.n_mu;
-				st[4] = res.alpha_p; st[5] = res.alpha_d; st[6] = res.sigma; st[7] = res.mu;
+		int mode = MODE_IDLE;
+		if (active) { // top of QP_SOLVE's loop (qpSWIFT.c:502-534)
+			int flag = -1;
+			if (iters >= prm.maxit) flag = 2; // QP_MAXIT (qpSWIFT.c:604-607)
+			else {
+				sc = ipm_residuals(pv, w.V, w.c, w.h, w.b, w.x, w.y, w.z, w.s, w.r, w.lam /* scratch: -(Px) */);
+				if (sc.n_rx < thr && sc.n_rz < thr && (p == 0 || sc.n_ry < thr) && sc.n_mu < prm.abstol) flag = 0;
+			}
+			if (flag >= 0) {
+				const size_t qi = (size_t)q;
+				warp_copy_out(io.x ? io.x + qi * n : nullptr, w.x, n);
+				if (p) warp_copy_out(io.y ? io.y + qi * p : nullptr, w.y, p);
+				warp_copy_out(io.z ? io.z + qi * m : nullptr, w.z, m);
+				warp_copy_out(io.s ? io.s + qi * m : nullptr, w.s, m);
+				if (lane == 0) {
+					if (io.flag) io.flag[q] = flag;
+					if (io.iters) io.iters[q] = iters;
+					if (io.fval) io.fval[q] = sc.fval;
+					if (io.stat) {
+						double *st = io.stat + qi * 8;
+						st[0] = sc.n_rx; st[1] = sc.n_ry; st[2] = sc.n_rz; st[3] = sc.n_mu;
+						st[4] = ap; st[5] = ad; st[6] = sigma; st[7] = mu;
+					}
+				}
+				__syncwarp();
+				active = false;
+			} else {
+				__syncwarp();
+				mu = ipm_lambda_mu(m, w);
+				if (sigma > prm.sigma_d) { // predictor: ds = -lambda^2 (qpSWIFT.c:540-552)
+					for (int i = lane; i < m; i += 32) w.ds[i] = -w.lam[i] * w.lam[i];
+					mode = MODE_PRED;
+				} else {                   // centering step only (qpSWIFT.c:572-579)
+					sigma = prm.sigma_d;
+					const double sm = sigma * mu;
+					for (int i = lane; i < m; i += 32) w.ds[i] = -(w.lam[i] * w.lam[i]) + sm;
+					mode = MODE_CENT;
+				}
+				ipm_update_kkt(m, w);
+				__syncwarp();
+				ipm_rhs(pv, w.r, w.ds, w.z, w.rhs);
 			}
 		}
-		__syncwarp();
+		if (!active) { // next QP: load its value row, set up kkt_initialize's system
+			if (lane == 0) q = atomicAdd(counter, 1);
+			q = __shfl_sync(0xffffffffu, q, 0);
+			if (q < io.count) {
+				const size_t qi = (size_t)q;
+				warp_copy_in(w.V, io.Ppr + qi * pv.offA, pv.offA);
+				if (p) warp_copy_in(w.V + pv.offA, io.Apr + qi * (pv.offG - pv.offA), pv.offG - pv.offA);
+				warp_copy_in(w.V + pv.offG, io.Gpr + qi * (pv.nV - pv.offG), pv.nV - pv.offG);
+				warp_copy_in(w.c, io.c + qi * n, n);
+				warp_copy_in(w.h, io.h + qi * m, m);
+				if (p) warp_copy_in(w.b, io.b + qi * p, p);
+				__syncwarp();
+				ipm_init_rhs(pv, w);
+				iters = 0;
+				sigma = prm.sigma0;
+				mu = ap = ad = 0.0;
+				mode = MODE_INIT;
+			}
+		}
+		if (!__syncthreads_or(mode != MODE_IDLE)) break;
+
+		if (mode != MODE_IDLE) {
+			run_segment(pg.words, pg.f_first, pg.f_waves, S);
+			run_segment(pg.words, pg.s_first, pg.s_waves, S);
+		}
+		if (mode == MODE_INIT) {
+			ipm_init_point(pv, w);
+			active = true;
+		} else if (mode == MODE_PRED) { // affine step length, sigma, corrector right-hand side (qpSWIFT.c:564-570)
+			ipm_recover_dz_ds(pv, w);
+			ipm_steplength(m, w.s, w.dsl, w.z, w.dz, ap, ad);
+			sigma = ipm_sigma(m, w, ap, ad, prm.sigma_d);
+			const double sm = sigma * mu;
+			for (int i = lane; i < m; i += 32) w.ds[i] = -(w.lam[i] * w.lam[i]) - (w.dsl[i] * w.dz[i]) + sm;
+			__syncwarp();
+			ipm_rhs(pv, w.r, w.ds, w.z, w.rhs);
+		}
+		__syncthreads(); // re-align the warps before they stream the solve schedule again
+		if (mode == MODE_PRED) run_segment(pg.words, pg.s_first, pg.s_waves, S);
+		if (mode == MODE_PRED || mode == MODE_CENT) { // step, damping, update (qpSWIFT.c:584-596)
+			ipm_recover_dz_ds(pv, w);
+			ipm_steplength(m, w.s, w.dsl, w.z, w.dz, ap, ad);
+			ap = ((0.99 * ap) < (1.0)) ? (0.99 * ap) : (1.0);
+			ad = ((0.99 * ad) < (1.0)) ? (0.99 * ad) : (1.0);
+			for (int i = lane; i < n; i += 32) w.x[i] += w.rhs[i] * ap;
+			for (int i = lane; i < p; i += 32) w.y[i] += w.rhs[n + i] * ad;
+			for (int i = lane; i < m; i += 32) { w.s[i] += w.dsl[i] * ap; w.z[i] += w.dz[i] * ad; }
+			__syncwarp();
+			++iters;
+		}
 	}
 }
 
-// LDL_numeric alone: value row + (z,z) diagonal from HBM, factor to HBM.
-__global__ void __launch_bounds__(32) ldl_numeric_kernel(const int *__restrict__ plan, const double *__restrict__ vals, const double *__restrict__ zdiag, double *__restrict__ Lx, double *__restrict__ D, int count, int *__restrict__ counter)
+// LDL_numeric alone: value row + (z,z) diagonal from HBM, factor to HBM.  One warp per CTA.
+__global__ void __launch_bounds__(32) ldl_numeric_kernel(const int *__restrict__ plan, ProgramView pg, SliceLayout lay, const double *__restrict__ vals, const double *__restrict__ zdiag, double *__restrict__ Lx, double *__restrict__ D, int count, int *__restrict__ counter)
 {
 	extern __shared__ __align__(16) double smem[];
 	const PlanView pv = view_of(plan);
 	const int lane = lane_id();
-	// layout: V[nV+pad] | zd[m] (as -zd/1 trick is NOT used: we store s = -zdiag, z = 1) | Lx | D | Y
-	const int nVp = (pv.nV + 1) & ~1;
-	double *V = smem, *sv = V + nVp, *zv = sv + pv.m, *L = zv + pv.m + ((2 * pv.m) & 1), *Dd = L + pv.lnz + (pv.lnz & 1), *Y = Dd + pv.N;
+	double *S = smem;
+	if (lane == 0) { S[lay.zero] = 0.0; S[lay.zero + 1] = -0.0; }
 	for (;;) {
 		int q = 0;
 		if (lane == 0) q = atomicAdd(counter, 1);
 		q = __shfl_sync(0xffffffffu, q, 0);
 		if (q >= count) break;
 		const size_t qi = (size_t)q;
-		warp_copy_in(V, vals + qi * pv.nV, pv.nV);
-		// -s/z with z = 1 and s = -d reproduces d exactly: -(-d)/1 == d
-		for (int i = lane; i < pv.m; i += 32) { sv[i] = -__ldg(zdiag + qi * pv.m + i); zv[i] = 1.0; }
+		warp_copy_in(S + lay.V, vals + qi * pv.nV, pv.nV);
+		warp_copy_in(S + lay.zd, zdiag + qi * pv.m, pv.m);
 		__syncwarp();
-		ldl_factor(pv, V, sv, zv, 0.0, L, Dd, Y);
-		warp_copy_out(Lx + qi * pv.lnz, L, pv.lnz);
-		warp_copy_out(D + qi * pv.N, Dd, pv.N);
+		run_segment(pg.words, pg.f_first, pg.f_waves, S);
+		warp_copy_out(Lx + qi * pv.lnz, S + lay.Lx, pv.lnz);
+		warp_copy_out(D + qi * pv.N, S + lay.D, pv.N);
 		__syncwarp();
 	}
 }
 
 // LDL_perm + lsolve + dsolve + ltsolve + permt alone.
-__global__ void __launch_bounds__(32) ldl_solve_kernel(const int *__restrict__ plan, const double *__restrict__ Lx, const double *__restrict__ D, const double *__restrict__ rhs, double *__restrict__ sol, int count, int *__restrict__ counter)
+__global__ void __launch_bounds__(32) ldl_solve_kernel(const int *__restrict__ plan, ProgramView pg, SliceLayout lay, const double *__restrict__ Lx, const double *__restrict__ D, const double *__restrict__ rhs, double *__restrict__ sol, int count, int *__restrict__ counter)
 {
 	extern __shared__ __align__(16) double smem[];
 	const PlanView pv = view_of(plan);
 	const int lane = lane_id();
-	double *L = smem, *Dd = L + pv.lnz + (pv.lnz & 1), *r = Dd + pv.N + (pv.N & 1), *wk = r + pv.N + (pv.N & 1);
+	double *S = smem;
+	if (lane == 0) { S[lay.zero] = 0.0; S[lay.zero + 1] = -0.0; }
 	for (;;) {
 		int q = 0;
 		if (lane == 0) q = atomicAdd(counter, 1);
 		q = __shfl_sync(0xffffffffu, q, 0);
 		if (q >= count) break;
 		const size_t qi = (size_t)q;
-		warp_copy_in(L, Lx + qi * pv.lnz, pv.lnz);
-		warp_copy_in(Dd, D + qi * pv.N, pv.N);
-		warp_copy_in(r, rhs + qi * pv.N, pv.N);
+		warp_copy_in(S + lay.Lx, Lx + qi * pv.lnz, pv.lnz);
+		warp_copy_in(S + lay.D, D + qi * pv.N, pv.N);
+		warp_copy_in(S + lay.rhs, rhs + qi * pv.N, pv.N);
 		__syncwarp();
-		ldl_solve(pv, L, Dd, r, wk);
-		warp_copy_out(sol + qi * pv.N, r, pv.N);
+		run_segment(pg.words, pg.s_first, pg.s_waves, S);
+		warp_copy_out(sol + qi * pv.N, S + lay.rhs, pv.N);
 		__syncwarp();
 	}
-}
-
-static SmemLayout make_layout(const Plan &pl)
-{
-	SmemLayout L;
-	int at = 0;
-	auto take = [&](long count) { int here = at; at += (int)((count + 1) & ~1L); return here; }; // keep 16-byte alignment
-	const long nV = pl.nnzP + pl.nnzA + pl.nnzG, N = pl.N, lnz = pl.Lp[pl.N];
-	L.V = take(nV); L.c = take(pl.n); L.h = take(pl.m); L.b = take(pl.p);
-	L.Lx = take(lnz); L.D = take(N); L.Y = take(N); L.rhs = take(N);
-	L.x = take(pl.n); L.y = take(pl.p); L.z = take(pl.m); L.s = take(pl.m);
-	L.r = take(N);
-	L.lam = take(pl.m > pl.n ? pl.m : pl.n); L.ds = take(pl.m); L.dz = take(pl.m); L.dsl = take(pl.m);
-	L.total = at;
-	return L;
 }
 
 } // namespace qpb
@@ -148,14 +221,17 @@ using namespace qpb;
 struct QPBatch
 {
 	Plan plan;
+	Program program;
 	double sigma_d = 0.0;
 	long capacity = 0;
 	int device = 0;
 	int sm_count = 0;
 	int *d_plan = nullptr;
+	uint2 *d_prog = nullptr;
 	int *d_counter = nullptr;
-	SmemLayout layout;
-	int ctas_per_sm = 1;
+	ProgramView pview;
+	int max_warps = 1;      // slices of shared memory that fit next to each other in one CTA
+	size_t smem_limit = 0;
 	// device staging for the host-pointer entry point
 	double *d_in[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	double *d_x = nullptr, *d_y = nullptr, *d_z = nullptr, *d_s = nullptr, *d_fval = nullptr, *d_stat = nullptr;
@@ -179,18 +255,22 @@ static int batch_alloc(QPBatch *B)
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, B->device));
 	B->sm_count = prop.multiProcessorCount;
-	B->layout = make_layout(pl);
-	const size_t smem = (size_t)B->layout.total * sizeof(double);
-	if (smem > (size_t)prop.sharedMemPerBlockOptin) return fail(QPB_E_PATTERN, "pattern does not fit in shared memory", cudaSuccess);
-	CUDA_TRY(cudaFuncSetAttribute(qp_solve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	CUDA_TRY(cudaFuncSetAttribute(ldl_numeric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-	CUDA_TRY(cudaFuncSetAttribute(ldl_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-	int occ = 0;
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qp_solve_fused_kernel, 32, smem));
-	B->ctas_per_sm = occ > 0 ? occ : 1;
+	const size_t slice = (size_t)B->program.lay.total * sizeof(double);
+	B->smem_limit = (size_t)prop.sharedMemPerBlockOptin;
+	if (slice > B->smem_limit) return fail(QPB_E_PATTERN, "pattern does not fit in shared memory", cudaSuccess);
+	B->max_warps = (int)std::min<size_t>(MAX_WARPS_PER_CTA, B->smem_limit / slice);
+	CUDA_TRY(cudaFuncSetAttribute(qp_solve_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
+	CUDA_TRY(cudaFuncSetAttribute(ldl_numeric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
+	CUDA_TRY(cudaFuncSetAttribute(ldl_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
 
 	CUDA_TRY(cudaMalloc(&B->d_plan, pl.blob.size() * sizeof(int32_t)));
 	CUDA_TRY(cudaMemcpy(B->d_plan, pl.blob.data(), pl.blob.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+	const Program &pg = B->program;
+	CUDA_TRY(cudaMalloc(&B->d_prog, pg.words.size() * sizeof(uint64_t)));
+	CUDA_TRY(cudaMemcpy(B->d_prog, pg.words.data(), pg.words.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+	B->pview.words = B->d_prog;
+	B->pview.f_first = pg.factor.first; B->pview.f_waves = pg.factor.waves;
+	B->pview.s_first = pg.solve.first; B->pview.s_waves = pg.solve.waves;
 	CUDA_TRY(cudaMalloc(&B->d_counter, 64 * sizeof(int)));
 	CUDA_TRY(cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking));
 	CUDA_TRY(cudaEventCreate(&B->ev0));
@@ -228,11 +308,14 @@ static int launch_fused(QPBatch *B, const BatchIO &io, const settings *opts, cud
 	prm.sigma0 = opts->sigma;
 	prm.sigma_d = B->sigma_d;
 	CUDA_TRY(cudaMemsetAsync(B->d_counter, 0, sizeof(int), st));
-	long grid = (long)B->sm_count * B->ctas_per_sm;
-	if (grid > io.count) grid = io.count;
-	if (grid < 1) grid = 1;
-	const size_t smem = (size_t)B->layout.total * sizeof(double);
-	qp_solve_fused_kernel<<<(unsigned)grid, 32, smem, st>>>(B->d_plan, B->layout, io, prm, B->d_counter);
+	// one persistent CTA per SM; small batches spread over the SMs with fewer warps per CTA
+	long warps = (io.count + B->sm_count - 1) / B->sm_count;
+	if (warps > B->max_warps) warps = B->max_warps;
+	if (warps < 1) warps = 1;
+	long grid = (io.count + warps - 1) / warps;
+	if (grid > B->sm_count) grid = B->sm_count;
+	const size_t smem = (size_t)warps * B->program.lay.total * sizeof(double);
+	qp_solve_cta_kernel<<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->d_plan, B->pview, B->program.lay, io, prm, B->d_counter);
 	CUDA_TRY(cudaGetLastError());
 	B->last_launches = 1;
 	return 0;
@@ -254,7 +337,9 @@ QPBatch *QPB_BATCH_CREATE(const QPBPlan *plan, qp_real sigma_d, qp_int capacity,
 	if (!plan || capacity < 1) { g_last_error = "QPB_BATCH_CREATE: bad argument"; return nullptr; }
 	if (!plan->plan.valid) { g_last_error = "QPB_BATCH_CREATE: unusable pattern (an inequality row is empty)"; return nullptr; }
 	QPBatch *B = new QPBatch;
+	if (!plan->program.ok) { g_last_error = "QPB_BATCH_CREATE: " + plan->program.error; return nullptr; }
 	B->plan = plan->plan;
+	B->program = plan->program;
 	B->sigma_d = sigma_d;
 	B->capacity = capacity;
 	B->device = device;
@@ -267,7 +352,7 @@ QPBatch *QP_SETUP_BATCH(const QP *proto, qp_int capacity, int device)
 	if (!proto) { g_last_error = "QP_SETUP_BATCH: null prototype"; return nullptr; }
 	QPBPlan tmp;
 	const smat *A = proto->A;
-	build_plan(tmp.plan, proto->n, proto->m, proto->p, proto->P->jc, proto->P->ir, A ? A->jc : nullptr, A ? A->ir : nullptr, proto->G->jc, proto->G->ir, proto->kkt ? proto->kkt->P : nullptr);
+	qpb_build(tmp, proto->n, proto->m, proto->p, proto->P->jc, proto->P->ir, A ? A->jc : nullptr, A ? A->ir : nullptr, proto->G->jc, proto->G->ir, proto->kkt ? proto->kkt->P : nullptr);
 	return QPB_BATCH_CREATE(&tmp, proto->sigma_d, capacity, device);
 }
 
@@ -276,6 +361,7 @@ void QP_CLEANUP_BATCH(QPBatch *B)
 	if (!B) return;
 	cudaSetDevice(B->device);
 	cudaFree(B->d_plan);
+	cudaFree(B->d_prog);
 	cudaFree(B->d_counter);
 	for (int i = 0; i < 6; ++i) cudaFree(B->d_in[i]);
 	cudaFree(B->d_x); cudaFree(B->d_y); cudaFree(B->d_z); cudaFree(B->d_s);
@@ -368,16 +454,14 @@ qp_int QPB_LDL_NUMERIC_BATCH(QPBatch *B, qp_int count, const qp_real *dvals, con
 	if (!B || count < 0 || !dvals || !dzdiag || !dLx || !dD) return fail(QPB_E_ARG, "QPB_LDL_NUMERIC_BATCH: bad argument", cudaSuccess);
 	if (count == 0) return 0;
 	CUDA_TRY(cudaSetDevice(B->device));
-	const Plan &pl = B->plan;
-	const long nV = pl.nnzP + pl.nnzA + pl.nnzG, lnz = pl.Lp[pl.N];
-	const size_t smem = (size_t)(((nV + 1) & ~1L) + 2 * pl.m + ((2 * pl.m) & 1) + lnz + (lnz & 1) + 2 * pl.N + 2) * sizeof(double);
+	const size_t smem = (size_t)B->program.lay.total * sizeof(double);
 	cudaStream_t st = (cudaStream_t)stream;
 	CUDA_TRY(cudaMemsetAsync(B->d_counter + 16, 0, sizeof(int), st));
 	int occ = 0;
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ldl_numeric_kernel, 32, smem));
 	long grid = (long)B->sm_count * (occ > 0 ? occ : 1);
 	if (grid > count) grid = count;
-	ldl_numeric_kernel<<<(unsigned)grid, 32, smem, st>>>(B->d_plan, dvals, dzdiag, dLx, dD, (int)count, B->d_counter + 16);
+	ldl_numeric_kernel<<<(unsigned)grid, 32, smem, st>>>(B->d_plan, B->pview, B->program.lay, dvals, dzdiag, dLx, dD, (int)count, B->d_counter + 16);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }
@@ -387,16 +471,14 @@ qp_int QPB_LDL_SOLVE_BATCH(QPBatch *B, qp_int count, const qp_real *dLx, const q
 	if (!B || count < 0 || !dLx || !dD || !drhs || !dsol) return fail(QPB_E_ARG, "QPB_LDL_SOLVE_BATCH: bad argument", cudaSuccess);
 	if (count == 0) return 0;
 	CUDA_TRY(cudaSetDevice(B->device));
-	const Plan &pl = B->plan;
-	const long lnz = pl.Lp[pl.N];
-	const size_t smem = (size_t)(lnz + (lnz & 1) + 3 * (pl.N + (pl.N & 1))) * sizeof(double);
+	const size_t smem = (size_t)B->program.lay.total * sizeof(double);
 	cudaStream_t st = (cudaStream_t)stream;
 	CUDA_TRY(cudaMemsetAsync(B->d_counter + 32, 0, sizeof(int), st));
 	int occ = 0;
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ldl_solve_kernel, 32, smem));
 	long grid = (long)B->sm_count * (occ > 0 ? occ : 1);
 	if (grid > count) grid = count;
-	ldl_solve_kernel<<<(unsigned)grid, 32, smem, st>>>(B->d_plan, dLx, dD, drhs, dsol, (int)count, B->d_counter + 32);
+	ldl_solve_kernel<<<(unsigned)grid, 32, smem, st>>>(B->d_plan, B->pview, B->program.lay, dLx, dD, drhs, dsol, (int)count, B->d_counter + 32);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }

@@ -4,10 +4,15 @@
 
 #include "qpswift_b200.h"
 #include "plan.h"
+#include "program.h"
 
 struct QPBPlan
 {
 	qpb::Plan plan;
+	qpb::Program program; // factor / solve schedules compiled from the plan (program.h)
 };
+
+// build_plan + build_program; returns plan.valid && program.ok
+bool qpb_build(QPBPlan &h, qp_int n, qp_int m, qp_int p, const qp_int *Pjc, const qp_int *Pir, const qp_int *Ajc, const qp_int *Air, const qp_int *Gjc, const qp_int *Gir, const qp_int *Permut);
 
 #endif

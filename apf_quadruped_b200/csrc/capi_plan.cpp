@@ -4,12 +4,18 @@
 
 using namespace qpb;
 
+bool qpb_build(QPBPlan &h, qp_int n, qp_int m, qp_int p, const qp_int *Pjc, const qp_int *Pir, const qp_int *Ajc, const qp_int *Air, const qp_int *Gjc, const qp_int *Gir, const qp_int *Permut)
+{
+	if (!build_plan(h.plan, n, m, p, Pjc, Pir, Ajc, Air, Gjc, Gir, Permut)) return false;
+	return build_program(h.plan, h.program);
+}
+
 extern "C" {
 
 QPBPlan *QPB_PLAN_CREATE(qp_int n, qp_int m, qp_int p, const qp_int *Pjc, const qp_int *Pir, const qp_int *Ajc, const qp_int *Air, const qp_int *Gjc, const qp_int *Gir, const qp_int *Permut)
 {
 	QPBPlan *h = new QPBPlan;
-	build_plan(h->plan, n, m, p, Pjc, Pir, Ajc, Air, Gjc, Gir, Permut);
+	qpb_build(*h, n, m, p, Pjc, Pir, Ajc, Air, Gjc, Gir, Permut);
 	return h;
 }
 
@@ -34,6 +40,25 @@ const qp_int *QPB_PLAN_ARRAY(const QPBPlan *h, int which, qp_int *count)
 	return v->data();
 }
 
+static qp_int qpb_segment_stat(const Segment &s, int which)
+{
+	switch (which) {
+	case 0: return s.waves;           // padded wave count the kernel executes
+	case 1: return s.stats.mul_waves; // multiply-subtract waves
+	case 2: return s.stats.div_waves; // quotient waves
+	case 3: return s.stats.terms;     // multiply-subtract operations (== the reference's)
+	case 4: return s.stats.divs;
+	case 5: return s.stats.chains;
+	case 6: return s.stats.lane_slots;
+	case 7: return s.stats.temps;
+	case 8: return s.stats.sum_waves;   // ordered-sum waves
+	case 9: return s.stats.sums;
+	case 10: return s.stats.suspensions; // accumulators parked in scratch and resumed
+	case 11: return s.first;             // first wave inside the program
+	default: return -1;
+	}
+}
+
 qp_int QPB_PLAN_INFO(const QPBPlan *h, int what)
 {
 	const Plan &pl = h->plan;
@@ -46,8 +71,28 @@ qp_int QPB_PLAN_INFO(const QPBPlan *h, int what)
 	case QPB_INFO_NNZU: return (qp_int)pl.scat_dst.size();
 	case QPB_INFO_VALID: return pl.valid ? 1 : 0;
 	case QPB_INFO_PLAN_WORDS: return (qp_int)pl.blob.size();
-	default: return -1;
+	case QPB_INFO_PROGRAM_OK: return h->program.ok ? 1 : 0;
+	case QPB_INFO_SLICE_DOUBLES: return h->program.lay.total;
+	case QPB_INFO_PROGRAM_WORDS: return (qp_int)h->program.words.size();
+	default: break;
 	}
+	if (what >= QPB_INFO_FACTOR_STATS && what < QPB_INFO_FACTOR_STATS + 16) return qpb_segment_stat(h->program.factor, what - QPB_INFO_FACTOR_STATS);
+	if (what >= QPB_INFO_SOLVE_STATS && what < QPB_INFO_SOLVE_STATS + 16) return qpb_segment_stat(h->program.solve, what - QPB_INFO_SOLVE_STATS);
+	return -1;
+}
+
+const unsigned long long *QPB_PLAN_PROGRAM(const QPBPlan *h, qp_int *words)
+{
+	if (words) *words = (qp_int)h->program.words.size();
+	return reinterpret_cast<const unsigned long long *>(h->program.words.data());
+}
+
+qp_int QPB_PLAN_LAYOUT(const QPBPlan *h, int *out, int capacity)
+{
+	const int count = (int)(sizeof(SliceLayout) / sizeof(int32_t));
+	const int32_t *src = reinterpret_cast<const int32_t *>(&h->program.lay);
+	for (int i = 0; i < count && i < capacity; ++i) out[i] = src[i];
+	return count;
 }
 
 qp_int QPB_AMD_ORDER(qp_int n, const qp_int *Ap, const qp_int *Ai, qp_int *Perm)

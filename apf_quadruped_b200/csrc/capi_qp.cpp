@@ -60,7 +60,7 @@ std::shared_ptr<CachedPlan> plan_for(qp_int n, qp_int m, qp_int p, const qp_int 
 	for (auto &cand : g_plans[h])
 		if (cand->key == key) return cand;
 	auto made = std::make_shared<CachedPlan>();
-	qpb::build_plan(made->handle.plan, n, m, p, Pjc, Pir, p ? Ajc : nullptr, p ? Air : nullptr, Gjc, Gir, Permut);
+	qpb_build(made->handle, n, m, p, Pjc, Pir, p ? Ajc : nullptr, p ? Air : nullptr, Gjc, Gir, Permut);
 	made->key.swap(key);
 	g_plans[h].push_back(made);
 	return made;

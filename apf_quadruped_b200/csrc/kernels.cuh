@@ -8,20 +8,24 @@
 // from order-independent reductions (min / max); every sum the reference accumulates sequentially
 // is accumulated sequentially here too.
 //
+// The factorisation and the triangular solves are not coded as loops: the host compiles them, per
+// sparsity pattern, into wave schedules (program.h) that run_segment() below interprets.
+//
 // Reference routines restated (dogbot_controller/src/qpSWIFT/):
 //   kkt_initialize Auxilary.c:992-1089      ipm_initial_point
 //   computeresiduals 745-786, obj_value 1133-1141   ipm_residuals
 //   formlambda 638-646, form_ds 315-345, updatekktmatrix 205-233, updatekktmatrix_b 274-295
 //   kktsolve_1/2 471-564, findsteplength 359-393, formrho 879-892, updatevariables 246-254
-//   LDL_numeric ldl.c:253-326               ldl_factor
-//   LDL_perm/lsolve/dsolve/ltsolve/permt ldl.c:495-597   ldl_solve
-//   QP_SOLVE qpSWIFT.c:473-644              ipm_solve
+//   LDL_numeric ldl.c:253-326               run_segment(factor schedule)
+//   LDL_perm/lsolve/dsolve/ltsolve/permt ldl.c:495-597   run_segment(solve schedule)
+//   QP_SOLVE qpSWIFT.c:473-644              qp_solve_cta_kernel (batch.cu)
 #pragma once
 
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "plan.h"
+#include "program.h"
 
 namespace qpb {
 
@@ -29,17 +33,6 @@ struct SolveParams
 {
 	int maxit;
 	double reltol, abstol, sigma0, sigma_d;
-};
-
-// Per-warp shared-memory layout, in doubles from the warp's base.
-struct SmemLayout
-{
-	int V, c, h, b;      // value row: P|A|G values, then c, h, b
-	int Lx, D, Y, rhs;   // factor, work vector, right-hand side / solution
-	int x, y, z, s;      // iterate
-	int r;               // residuals [rx; ry; rz]
-	int lam, ds, dz, dsl;
-	int total;           // doubles per warp
 };
 
 struct BatchIO
@@ -117,86 +110,72 @@ __device__ __forceinline__ void warp_copy_out(double *__restrict__ dst, const do
 }
 
 // ------------------------------------------------------------------------------------------------
-// LDL_numeric (ldl.c:253-326), up-looking, one pivot row at a time.
-//   V      : the QP's value row (P|A|G) in shared memory
-//   zd     : (z,z) diagonal source; zd_const != 0 -> every diagonal is zd_const (the -I of
-//            kkt_initialize), else the diagonal of inequality i is -s[i]/z[i] (updatekktmatrix,
-//            Auxilary.c:211-215)
-// The column update  Y[Li[p]] -= Lx[p]*yi  touches distinct targets, so the lanes split it; the
-// pivot recurrence  D[k] -= l_ki*yi  is carried redundantly by all lanes in the reference order.
+// Interpreter of the wave schedules (program.h).  `S` is the QP's slice of shared memory, `t` the
+// lane's accumulator.  The three wave kinds are warp-uniform, so the only divergence is predication.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ldl_factor(const PlanView &pv, const double *V, const double *sv, const double *zv, double zd_const, double *Lx, double *D, double *Y)
+__device__ __forceinline__ double regularise(double dk) // ldl.c:319-320
 {
-	const int lane = lane_id();
-	for (int i = lane; i < pv.N; i += 32) Y[i] = 0.0;
-	__syncwarp();
-	for (int k = 0; k < pv.N; ++k) {
-		const int s0 = __ldg(pv.scat_ptr + k), s1 = __ldg(pv.scat_ptr + k + 1);
-		for (int t = s0 + lane; t < s1; t += 32) {
-			const int dst = __ldg(pv.scat_dst + t), src = __ldg(pv.scat_src + t);
-			double val;
-			if (src < pv.nV) val = V[src];
-			else if (zd_const != 0.0) val = zd_const;
-			else val = -sv[src - pv.nV] / zv[src - pv.nV];
-			Y[dst] += val;
+	const double sign = dk <= 0.0 ? -1.0 : 1.0;
+	return (sign * dk <= 0.00000000000001) ? sign * 0.0000001 : dk;
+}
+
+__device__ __forceinline__ void exec_wave(const uint2 ins, double &t, double *__restrict__ S)
+{
+	const unsigned lo = ins.x, hi = ins.y;
+	const unsigned M = (1u << INS_ADDR_BITS) - 1u;
+	if (hi & 0xC0000000u) {
+		if (hi & 0x80000000u) { // quotients
+			if (hi & 0x8000u) S[(hi >> 16) & M] = S[lo & M] / S[(lo >> 16) & M];
+		} else {                // ordered sums: t = S[ci]; t -= S[a+i], i ascending
+			const int cnt = (hi & 0x8000u) ? (int)((lo >> 16) & M) : 0;
+			const int most = __reduce_max_sync(0xffffffffu, cnt);
+			const double *src = S + (lo & M);
+			double acc = S[hi & M];
+#pragma unroll 4
+			for (int i = 0; i < most; ++i)
+				if (i < cnt) acc = acc - src[i];
+			if (cnt) S[(hi >> 16) & M] = acc;
 		}
-		__syncwarp();
-		double dk = Y[k];
-		__syncwarp();
-		if (lane == 0) Y[k] = 0.0;
-		const int p0 = __ldg(pv.pat_ptr + k), p1 = __ldg(pv.pat_ptr + k + 1);
-		for (int t = p0; t < p1; ++t) {
-			const int i = __ldg(pv.pat_col + t), slot = __ldg(pv.pat_slot + t);
-			const double yi = Y[i];
-			__syncwarp();
-			for (int q = __ldg(pv.lp + i) + lane; q < slot; q += 32) Y[__ldg(pv.li + q)] -= Lx[q] * yi;
-			const double l = yi / D[i];
-			dk -= l * yi;
-			if (lane == 0) { Y[i] = 0.0; Lx[slot] = l; }
-			__syncwarp();
-		}
-		const double sign = dk <= 0.0 ? -1.0 : 1.0;          // dynamic regularisation, ldl.c:319-320
-		dk = (sign * dk <= 0.00000000000001) ? sign * 0.0000001 : dk;
-		if (lane == 0) D[k] = dk;
-		__syncwarp();
+	} else {                    // one term of up to 32 chains
+		const double va = S[lo & M], vb = S[(lo >> 16) & M];
+		if (lo & 0x4000u) // FIRST: t = init + (+0.0 | -0.0)
+			t = S[hi & M] + __hiloint2double((int)((lo << 1) & 0x80000000u), 0);
+		double prod = va * vb;
+		prod = __hiloint2double(__double2hiint(prod) ^ (int)((hi << 17) & 0x80000000u), __double2loint(prod)); // ADD: t - (-prod)
+		t = t - prod;
+		if (lo & 0x8000u) // LAST
+			S[(hi >> 16) & M] = (lo & 0x80000000u) ? regularise(t) : t;
 	}
 }
 
-// ------------------------------------------------------------------------------------------------
-// x = P' L'^-1 D^-1 L^-1 P b (ldl.c:495-597), in place on `rhs`, `w` is an N-vector of scratch.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ldl_solve(const PlanView &pv, const double *Lx, const double *D, double *rhs, double *w)
+// Runs waves [first, first + waves) of `prog` (waves is a multiple of PROGRAM_WAVE_PAD == 4).  The
+// next four instruction words of the lane are always in flight (read-only path, L1 resident
+// while the warps of a CTA run the same segment), so the loop never waits for global memory.
+__device__ __forceinline__ void run_segment(const uint2 *__restrict__ prog, int first, int waves, double *__restrict__ S)
 {
-	const int lane = lane_id();
-	const int N = pv.N;
-	for (int j = lane; j < N; j += 32) w[j] = rhs[__ldg(pv.perm + j)];
-	__syncwarp();
-	for (int j = 0; j < N; ++j) {                              // forward: column scatter
-		const int q0 = __ldg(pv.lp + j), q1 = __ldg(pv.lp + j + 1);
-		if (q0 == q1) continue;
-		const double xj = w[j];
-		for (int q = q0 + lane; q < q1; q += 32) w[__ldg(pv.li + q)] -= Lx[q] * xj;
+	const uint2 *p = prog + (size_t)first * 32 + lane_id();
+	uint2 b0 = __ldg(p), b1 = __ldg(p + 32), b2 = __ldg(p + 64), b3 = __ldg(p + 96);
+	double t = 0.0;
+	for (int w = 4; w <= waves; w += 4) {
+		const bool more = w < waves;
+		const uint2 *nx = p + (size_t)w * 32;
+		uint2 c = b0;
+		if (more) b0 = __ldg(nx);
+		exec_wave(c, t, S);
+		__syncwarp();
+		c = b1;
+		if (more) b1 = __ldg(nx + 32);
+		exec_wave(c, t, S);
+		__syncwarp();
+		c = b2;
+		if (more) b2 = __ldg(nx + 64);
+		exec_wave(c, t, S);
+		__syncwarp();
+		c = b3;
+		if (more) b3 = __ldg(nx + 96);
+		exec_wave(c, t, S);
 		__syncwarp();
 	}
-	for (int j = lane; j < N; j += 32) w[j] /= D[j];
-	__syncwarp();
-	for (int j = N - 1; j >= 0; --j) {                         // backward: column gather, sequential sum
-		const int q0 = __ldg(pv.lp + j), q1 = __ldg(pv.lp + j + 1);
-		if (q0 == q1) continue;
-		// products in parallel, subtraction chain in the reference order by lane 0
-		double acc = w[j];
-		for (int base = q0; base < q1; base += 32) {
-			const int q = base + lane;
-			double t = 0.0;
-			if (q < q1) t = Lx[q] * w[__ldg(pv.li + q)];
-			const int cnt = min(32, q1 - base);
-			for (int u = 0; u < cnt; ++u) acc -= __shfl_sync(0xffffffffu, t, u);
-		}
-		if (lane == 0) w[j] = acc;
-		__syncwarp();
-	}
-	for (int j = lane; j < N; j += 32) rhs[__ldg(pv.perm + j)] = w[j];
-	__syncwarp();
 }
 
 struct Scalars
@@ -294,34 +273,41 @@ __device__ __forceinline__ void ipm_rhs(const PlanView &pv, const double *r, con
 
 struct WarpState
 {
-	double *V, *c, *h, *b, *Lx, *D, *Y, *rhs, *x, *y, *z, *s, *r, *lam, *ds, *dz, *dsl;
+	double *S; // slice base
+	double *V, *c, *h, *b, *zd, *rhs, *x, *y, *z, *s, *r, *lam, *ds, *dz, *dsl;
 };
 
-__device__ __forceinline__ WarpState carve(double *base, const SmemLayout &L)
+__device__ __forceinline__ WarpState carve(double *base, const SliceLayout &L)
 {
 	WarpState w;
-	w.V = base + L.V; w.c = base + L.c; w.h = base + L.h; w.b = base + L.b;
-	w.Lx = base + L.Lx; w.D = base + L.D; w.Y = base + L.Y; w.rhs = base + L.rhs;
+	w.S = base;
+	w.V = base + L.V; w.c = base + L.c; w.h = base + L.h; w.b = base + L.b; w.zd = base + L.zd;
+	w.rhs = base + L.rhs;
 	w.x = base + L.x; w.y = base + L.y; w.z = base + L.z; w.s = base + L.s;
 	w.r = base + L.r; w.lam = base + L.lam; w.ds = base + L.ds; w.dz = base + L.dz; w.dsl = base + L.dsl;
 	return w;
 }
 
-// kkt_initialize (Auxilary.c:992-1089)
-__device__ __forceinline__ void ipm_initial_point(const PlanView &pv, WarpState &w)
+// kkt_initialize, first half (Auxilary.c:1006-1030): rhs = [-c; b; h], (z,z) block = -I
+__device__ __forceinline__ void ipm_init_rhs(const PlanView &pv, WarpState &w)
 {
 	const int lane = lane_id();
 	const int n = pv.n, m = pv.m, p = pv.p;
 	for (int i = lane; i < n; i += 32) w.rhs[i] = -w.c[i];
 	for (int i = lane; i < p; i += 32) w.rhs[n + i] = w.b[i];
-	for (int i = lane; i < m; i += 32) w.rhs[n + p + i] = w.h[i];
+	for (int i = lane; i < m; i += 32) { w.rhs[n + p + i] = w.h[i]; w.zd[i] = -1.0; }
 	__syncwarp();
-	ldl_factor(pv, w.V, nullptr, nullptr, -1.0, w.Lx, w.D, w.Y);
-	ldl_solve(pv, w.Lx, w.D, w.rhs, w.Y);
+}
+
+// kkt_initialize, second half (Auxilary.c:1044-1083): x, y from the solution, r = h - G x,
+// s and z shifted into the cone.
+__device__ __forceinline__ void ipm_init_point(const PlanView &pv, WarpState &w)
+{
+	const int lane = lane_id();
+	const int n = pv.n, m = pv.m, p = pv.p;
 	for (int i = lane; i < n; i += 32) w.x[i] = w.rhs[i];
 	for (int i = lane; i < p; i += 32) w.y[i] = w.rhs[n + i];
 	__syncwarp();
-	// r = h - G x, its min and max
 	double lo = 0.0, hi = 0.0;
 	bool first = true;
 	double *zi = w.dz; // scratch
@@ -345,98 +331,47 @@ __device__ __forceinline__ void ipm_initial_point(const PlanView &pv, WarpState 
 	__syncwarp();
 }
 
-struct SolveResult
-{
-	int flag, iters;
-	Scalars sc;
-	double alpha_p, alpha_d, sigma, mu;
-};
-
-// QP_SOLVE main loop (qpSWIFT.c:499-607)
-__device__ __forceinline__ SolveResult ipm_solve(const PlanView &pv, WarpState &w, const SolveParams &prm)
+// lambda = sqrt(s.z), mu = lambda'lambda / m   (qpSWIFT.c:537-538)
+__device__ __forceinline__ double ipm_lambda_mu(int m, WarpState &w)
 {
 	const int lane = lane_id();
-	const int n = pv.n, m = pv.m, p = pv.p, np = n + p;
-	SolveResult res;
-	res.flag = 3; // QP_FATAL until proven otherwise (qpSWIFT.c:80)
-	res.iters = 0;
-	res.alpha_p = 0.0;
-	res.alpha_d = 0.0;
-	res.mu = 0.0;
-	double sigma = prm.sigma0;
-	const double thr = prm.reltol / sqrt(3.0);
-	for (int it = 0; it < prm.maxit; ++it) {
-		res.sc = ipm_residuals(pv, w.V, w.c, w.h, w.b, w.x, w.y, w.z, w.s, w.r, w.lam /* scratch: -(Px) */);
-		const bool small = res.sc.n_rx < thr && res.sc.n_rz < thr && (p == 0 || res.sc.n_ry < thr) && res.sc.n_mu < prm.abstol;
-		if (small) { res.flag = 0; break; }
+	for (int i = lane; i < m; i += 32) w.lam[i] = sqrt(w.s[i] * w.z[i]);
+	__syncwarp();
+	double mu = 0.0;
+	if (lane == 0) { for (int i = 0; i < m; ++i) mu += w.lam[i] * w.lam[i]; mu = mu / m; }
+	return __shfl_sync(0xffffffffu, mu, 0);
+}
 
-		// lambda = sqrt(s.z), mu = lambda'lambda / m   (qpSWIFT.c:537-538)
-		__syncwarp();
-		for (int i = lane; i < m; i += 32) w.lam[i] = sqrt(w.s[i] * w.z[i]);
-		__syncwarp();
-		double mu = 0.0;
-		if (lane == 0) { for (int i = 0; i < m; ++i) mu += w.lam[i] * w.lam[i]; mu = mu / m; }
-		mu = __shfl_sync(0xffffffffu, mu, 0);
-		res.mu = mu;
+// (z,z) block of the KKT matrix: -s/z   (updatekktmatrix, Auxilary.c:211-215)
+__device__ __forceinline__ void ipm_update_kkt(int m, WarpState &w)
+{
+	for (int i = lane_id(); i < m; i += 32) w.zd[i] = -w.s[i] / w.z[i];
+}
 
-		double ap, ad;
-		if (sigma > prm.sigma_d) {
-			// predictor: ds = -lambda^2, refactor with K_zz = -s/z, solve
-			for (int i = lane; i < m; i += 32) w.ds[i] = -w.lam[i] * w.lam[i];
-			__syncwarp();
-			ipm_rhs(pv, w.r, w.ds, w.z, w.rhs);
-			ldl_factor(pv, w.V, w.s, w.z, 0.0, w.Lx, w.D, w.Y);
-			ldl_solve(pv, w.Lx, w.D, w.rhs, w.Y);
-			for (int i = lane; i < m; i += 32) {
-				const double dzi = w.rhs[np + i];
-				w.dz[i] = dzi;
-				w.dsl[i] = (w.ds[i] - (w.s[i] * dzi)) / w.z[i];
-			}
-			__syncwarp();
-			ipm_steplength(m, w.s, w.dsl, w.z, w.dz, ap, ad);
-			// rho, sigma   (Auxilary.c:879-892, qpSWIFT.c:566-567)
-			double a = 0.0;
-			if (lane == 0) { for (int i = 0; i < m; ++i) a += (w.s[i] + (ap * w.dsl[i])) * (w.z[i] + (ad * w.dz[i])); }
-			else if (lane == 1) { for (int i = 0; i < m; ++i) a += w.s[i] * w.z[i]; }
-			const double num = __shfl_sync(0xffffffffu, a, 0), den = __shfl_sync(0xffffffffu, a, 1);
-			const double rho = num / den;
-			const double mr = (1 < rho) ? 1 : rho;
-			const double cube = mr * mr * mr;
-			sigma = (prm.sigma_d > cube) ? prm.sigma_d : cube;
-			// corrector right-hand side
-			const double sm = sigma * mu;
-			for (int i = lane; i < m; i += 32) w.ds[i] = -(w.lam[i] * w.lam[i]) - (w.dsl[i] * w.dz[i]) + sm;
-			__syncwarp();
-			ipm_rhs(pv, w.r, w.ds, w.z, w.rhs);
-		} else {
-			sigma = prm.sigma_d;
-			const double sm = sigma * mu;
-			for (int i = lane; i < m; i += 32) w.ds[i] = -(w.lam[i] * w.lam[i]) + sm;
-			__syncwarp();
-			ipm_rhs(pv, w.r, w.ds, w.z, w.rhs);
-			ldl_factor(pv, w.V, w.s, w.z, 0.0, w.Lx, w.D, w.Y);
-		}
-		ldl_solve(pv, w.Lx, w.D, w.rhs, w.Y);
-		for (int i = lane; i < m; i += 32) {
-			const double dzi = w.rhs[np + i];
-			w.dz[i] = dzi;
-			w.dsl[i] = (w.ds[i] - (w.s[i] * dzi)) / w.z[i];
-		}
-		__syncwarp();
-		ipm_steplength(m, w.s, w.dsl, w.z, w.dz, ap, ad);
-		ap = ((0.99 * ap) < (1.0)) ? (0.99 * ap) : (1.0);
-		ad = ((0.99 * ad) < (1.0)) ? (0.99 * ad) : (1.0);
-		res.alpha_p = ap;
-		res.alpha_d = ad;
-		for (int i = lane; i < n; i += 32) w.x[i] += w.rhs[i] * ap;
-		for (int i = lane; i < p; i += 32) w.y[i] += w.rhs[n + i] * ad;
-		for (int i = lane; i < m; i += 32) { w.s[i] += w.dsl[i] * ap; w.z[i] += w.dz[i] * ad; }
-		__syncwarp();
-		++res.iters;
+// delta_z from the solution, delta_s = (ds - s.delta_z)/z   (Auxilary.c:508-511, 556-562)
+__device__ __forceinline__ void ipm_recover_dz_ds(const PlanView &pv, WarpState &w)
+{
+	const int np = pv.n + pv.p;
+	for (int i = lane_id(); i < pv.m; i += 32) {
+		const double dzi = w.rhs[np + i];
+		w.dz[i] = dzi;
+		w.dsl[i] = (w.ds[i] - (w.s[i] * dzi)) / w.z[i];
 	}
-	if (res.iters == prm.maxit) res.flag = 2; // QP_MAXIT (qpSWIFT.c:604-607)
-	res.sigma = sigma;
-	return res;
+	__syncwarp();
+}
+
+// rho (Auxilary.c:879-892) and sigma = max(sigma_d, min(1,rho)^3) (qpSWIFT.c:566-567)
+__device__ __forceinline__ double ipm_sigma(int m, const WarpState &w, double ap, double ad, double sigma_d)
+{
+	const int lane = lane_id();
+	double a = 0.0;
+	if (lane == 0) { for (int i = 0; i < m; ++i) a += (w.s[i] + (ap * w.dsl[i])) * (w.z[i] + (ad * w.dz[i])); }
+	else if (lane == 1) { for (int i = 0; i < m; ++i) a += w.s[i] * w.z[i]; }
+	const double num = __shfl_sync(0xffffffffu, a, 0), den = __shfl_sync(0xffffffffu, a, 1);
+	const double rho = num / den;
+	const double mr = (1 < rho) ? 1 : rho;
+	const double cube = mr * mr * mr;
+	return (sigma_d > cube) ? sigma_d : cube;
 }
 
 #endif // __CUDACC__

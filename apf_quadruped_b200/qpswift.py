@@ -58,7 +58,8 @@ class QP(C.Structure):
 #: every symbol include/qpSWIFT/qpSWIFT.h and include/qpswift_b200.h declare
 EXPORTS = [
     "QP_SETUP", "QP_SETUP_dense", "QP_SOLVE", "QP_CLEANUP", "QP_CLEANUP_dense",
-    "QPB_PLAN_CREATE", "QPB_PLAN_DESTROY", "QPB_PLAN_ARRAY", "QPB_PLAN_INFO", "QPB_AMD_ORDER",
+    "QPB_PLAN_CREATE", "QPB_PLAN_DESTROY", "QPB_PLAN_ARRAY", "QPB_PLAN_INFO", "QPB_AMD_ORDER", "QPB_PLAN_PROGRAM",
+    "QPB_PLAN_LAYOUT",
     "QP_SETUP_BATCH", "QPB_BATCH_CREATE", "QP_SOLVE_BATCH", "QP_SOLVE_BATCH_DEVICE", "QP_CLEANUP_BATCH",
     "QPB_BATCH_READ_STATS", "QPB_BATCH_SET_SIGMA_D", "QPB_BATCH_LAST_KERNEL_MS", "QPB_BATCH_LAST_LAUNCHES",
     "QPB_LDL_NUMERIC_BATCH", "QPB_LDL_SOLVE_BATCH", "QPB_LAST_ERROR", "QPB_DEVICE_COUNT",
@@ -90,6 +91,10 @@ def lib():
         lb.QPB_PLAN_ARRAY.argtypes = [V, C.c_int, PL]
         lb.QPB_PLAN_INFO.restype = L
         lb.QPB_PLAN_INFO.argtypes = [V, C.c_int]
+        lb.QPB_PLAN_PROGRAM.restype = C.POINTER(C.c_uint64)
+        lb.QPB_PLAN_PROGRAM.argtypes = [V, PL]
+        lb.QPB_PLAN_LAYOUT.restype = L
+        lb.QPB_PLAN_LAYOUT.argtypes = [V, C.POINTER(C.c_int), C.c_int]
         lb.QPB_AMD_ORDER.restype = L
         lb.QPB_AMD_ORDER.argtypes = [L, PL, PL, PL]
         lb.QP_SETUP_BATCH.restype = V
@@ -156,7 +161,13 @@ class Plan:
     """Symbolic plan of one sparsity pattern (host only; no GPU needed)."""
 
     ARRAYS = {"Kjc": 0, "Kir": 1, "P": 2, "Pinv": 3, "Parent": 4, "Lnz": 5, "Lp": 6, "Li": 7}
-    INFO = {"N": 0, "nnzK": 1, "lnz": 2, "amd_status": 3, "factor_flops": 4, "nnzU": 5, "valid": 6, "plan_words": 7}
+    INFO = {"N": 0, "nnzK": 1, "lnz": 2, "amd_status": 3, "factor_flops": 4, "nnzU": 5, "valid": 6, "plan_words": 7,
+            "program_ok": 8, "slice_doubles": 9, "program_words": 10}
+    SEGMENT = {"factor": 32, "solve": 48}
+    SEGMENT_STATS = ["waves", "mul_waves", "div_waves", "terms", "divs", "chains", "lane_slots", "temps", "sum_waves",
+                     "sums", "suspensions", "first"]
+    LAYOUT = ["zero", "V", "c", "h", "b", "zd", "Lx", "D", "T", "rhs", "x", "y", "z", "s", "r", "lam", "ds", "dz", "dsl",
+              "total", "tsize"]
 
     def __init__(self, pattern, permut=None):
         self.pattern = pattern
@@ -177,6 +188,25 @@ class Plan:
 
     def info(self, name: str) -> int:
         return int(lib().QPB_PLAN_INFO(self.handle, self.INFO[name]))
+
+    def segment(self, which: str) -> dict:
+        """Statistics of the compiled ``factor`` / ``solve`` schedule (csrc/program.h)."""
+        base = self.SEGMENT[which]
+        return {n: int(lib().QPB_PLAN_INFO(self.handle, base + i)) for i, n in enumerate(self.SEGMENT_STATS)}
+
+    def layout(self) -> dict:
+        buf = (C.c_int * 32)()
+        cnt = int(lib().QPB_PLAN_LAYOUT(self.handle, buf, 32))
+        assert cnt == len(self.LAYOUT)
+        return {n: int(buf[i]) for i, n in enumerate(self.LAYOUT)}
+
+    def program(self) -> np.ndarray:
+        """The instruction words, shape (waves, 32), uint64."""
+        cnt = C.c_long()
+        ptr = lib().QPB_PLAN_PROGRAM(self.handle, C.byref(cnt))
+        if cnt.value == 0:
+            return np.zeros((0, 32), dtype=np.uint64)
+        return np.ctypeslib.as_array(ptr, shape=(cnt.value,)).copy().reshape(-1, 32)
 
     def close(self):
         if self.handle:

@@ -61,9 +61,24 @@ enum QPBPlanInfo
 	QPB_INFO_FACTOR_FLOPS = 4, /* sum Lnz_k (Lnz_k + 2), ldl.c:182-184 */
 	QPB_INFO_NNZU = 5,         /* upper-triangular KKT entries the factorisation reads */
 	QPB_INFO_VALID = 6,
-	QPB_INFO_PLAN_WORDS = 7 /* int32 words of the device plan */
+	QPB_INFO_PLAN_WORDS = 7, /* int32 words of the device plan */
+	QPB_INFO_PROGRAM_OK = 8,    /* 1 when the factor/solve schedules could be compiled */
+	QPB_INFO_SLICE_DOUBLES = 9, /* doubles of shared memory one QP occupies */
+	QPB_INFO_PROGRAM_WORDS = 10, /* 64-bit instruction words of the schedules */
+	/* per schedule, + {0 waves, 1 multiply-subtract waves, 2 quotient waves, 3 multiply-subtracts,
+	 * 4 quotients, 5 chains, 6 occupied lane slots, 7 scratch doubles, 8 ordered-sum waves,
+	 * 9 ordered sums, 10 suspensions, 11 first wave} */
+	QPB_INFO_FACTOR_STATS = 32,
+	QPB_INFO_SOLVE_STATS = 48
 };
 qp_int QPB_PLAN_INFO(const QPBPlan *plan, int what);
+
+/* The compiled factor / solve schedules (csrc/program.h): 64-bit instruction words, 32 per wave,
+ * and the layout of one QP's shared-memory slice as int32 offsets in doubles, in the order
+ * {zero, V, c, h, b, zd, Lx, D, T, rhs, x, y, z, s, r, lam, ds, dz, dsl, total, tsize}.
+ * Exposed so that the schedules can be checked on the host (tests/test_program.py). */
+const unsigned long long *QPB_PLAN_PROGRAM(const QPBPlan *plan, qp_int *words);
+qp_int QPB_PLAN_LAYOUT(const QPBPlan *plan, int *out, int capacity);
 
 /* The ordering alone (test hook for amd_l_order, amd_order.c:21-199): returns the AMD status
  * (0 ok, 1 ok-but-jumbled, -2 invalid) and writes Perm[n]. */

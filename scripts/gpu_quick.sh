@@ -1,11 +1,11 @@
 set -x
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
-python -m pytest tests -m gpu -x -q 2>&1 | tail -30
-python - <<'PY'
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -30
+timeout 600 python - <<'PY'
 import time, numpy as np, sys
 sys.path.insert(0,'.')
 from apf_quadruped_b200 import dogbot, qpswift as Q
-for kind, cnt in [('trot', 65536), ('stance', 32768), ('mpc', 8192)]:
+for kind, cnt in [('trot', 65536), ('stance', 32768), ('crawl', 32768), ('mpc', 8192)]:
     b = dogbot.generate(kind, cnt)
     s = Q.BatchSolver(b.pattern, cnt)
     for rep in range(3):
