@@ -45,7 +45,7 @@ static int fail(int code, const char *what, cudaError_t e)
 struct ProgramView
 {
 	const uint2 *words;
-	int f_first, f_waves, s_first, s_waves;
+	int f_first, f_waves, f_width, s_first, s_waves, s_width;
 };
 
 enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_PRED = 2, MODE_CENT = 3 };
@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_CTA * 32, 1) qp_solve_cta_kernel
 	const PlanView pv = view_of(plan);
 	const int lane = lane_id(), warp = threadIdx.x >> 5;
 	double *S = smem + (size_t)warp * lay.total;
+	const unsigned sb = (unsigned)__cvta_generic_to_shared(S);
 	WarpState w = carve(S, lay);
 	if (lane == 0) { S[lay.zero] = 0.0; S[lay.zero + 1] = -0.0; }
 	__syncwarp();
@@ -135,8 +136,8 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_CTA * 32, 1) qp_solve_cta_kernel
 		if (!__syncthreads_or(mode != MODE_IDLE)) break;
 
 		if (mode != MODE_IDLE) {
-			run_segment(pg.words, pg.f_first, pg.f_waves, S);
-			run_segment(pg.words, pg.s_first, pg.s_waves, S);
+			run_segment(pg.words, pg.f_first, pg.f_waves, pg.f_width, sb);
+			run_segment(pg.words, pg.s_first, pg.s_waves, pg.s_width, sb);
 		}
 		if (mode == MODE_INIT) {
 			ipm_init_point(pv, w);
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_CTA * 32, 1) qp_solve_cta_kernel
 			ipm_rhs(pv, w.r, w.ds, w.z, w.rhs);
 		}
 		__syncthreads(); // re-align the warps before they stream the solve schedule again
-		if (mode == MODE_PRED) run_segment(pg.words, pg.s_first, pg.s_waves, S);
+		if (mode == MODE_PRED) run_segment(pg.words, pg.s_first, pg.s_waves, pg.s_width, sb);
 		if (mode == MODE_PRED || mode == MODE_CENT) { // step, damping, update (qpSWIFT.c:584-596)
 			ipm_recover_dz_ds(pv, w);
 			ipm_steplength(m, w.s, w.dsl, w.z, w.dz, ap, ad);
@@ -183,7 +184,9 @@ __global__ void __launch_bounds__(32) ldl_numeric_kernel(const int *__restrict__
 		warp_copy_in(S + lay.V, vals + qi * pv.nV, pv.nV);
 		warp_copy_in(S + lay.zd, zdiag + qi * pv.m, pv.m);
 		__syncwarp();
-		run_segment(pg.words, pg.f_first, pg.f_waves, S);
+		run_segment(pg.words, pg.f_first, pg.f_waves, pg.f_width, (unsigned)__cvta_generic_to_shared(S));
+		for (int i = lane; i < pv.N; i += 32) S[lay.D + i] = regularise(S[lay.D + i]); // chains store raw pivots (program.h)
+		__syncwarp();
 		warp_copy_out(Lx + qi * pv.lnz, S + lay.Lx, pv.lnz);
 		warp_copy_out(D + qi * pv.N, S + lay.D, pv.N);
 		__syncwarp();
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(32) ldl_solve_kernel(const int *__restrict__ p
 		warp_copy_in(S + lay.D, D + qi * pv.N, pv.N);
 		warp_copy_in(S + lay.rhs, rhs + qi * pv.N, pv.N);
 		__syncwarp();
-		run_segment(pg.words, pg.s_first, pg.s_waves, S);
+		run_segment(pg.words, pg.s_first, pg.s_waves, pg.s_width, (unsigned)__cvta_generic_to_shared(S));
 		warp_copy_out(sol + qi * pv.N, S + lay.rhs, pv.N);
 		__syncwarp();
 	}
@@ -269,8 +272,8 @@ static int batch_alloc(QPBatch *B)
 	CUDA_TRY(cudaMalloc(&B->d_prog, pg.words.size() * sizeof(uint64_t)));
 	CUDA_TRY(cudaMemcpy(B->d_prog, pg.words.data(), pg.words.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
 	B->pview.words = B->d_prog;
-	B->pview.f_first = pg.factor.first; B->pview.f_waves = pg.factor.waves;
-	B->pview.s_first = pg.solve.first; B->pview.s_waves = pg.solve.waves;
+	B->pview.f_first = pg.factor.first; B->pview.f_waves = pg.factor.waves; B->pview.f_width = pg.factor.width;
+	B->pview.s_first = pg.solve.first; B->pview.s_waves = pg.solve.waves; B->pview.s_width = pg.solve.width;
 	CUDA_TRY(cudaMalloc(&B->d_counter, 64 * sizeof(int)));
 	CUDA_TRY(cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking));
 	CUDA_TRY(cudaEventCreate(&B->ev0));

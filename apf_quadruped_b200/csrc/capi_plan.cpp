@@ -54,7 +54,8 @@ static qp_int qpb_segment_stat(const Segment &s, int which)
 	case 8: return s.stats.sum_waves;   // ordered-sum waves
 	case 9: return s.stats.sums;
 	case 10: return s.stats.suspensions; // accumulators parked in scratch and resumed
-	case 11: return s.first;             // first wave inside the program
+	case 11: return s.first;             // offset inside the program, in units of 32 words
+	case 12: return s.width;             // instruction words per lane per super-wave
 	default: return -1;
 	}
 }

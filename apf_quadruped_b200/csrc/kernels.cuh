@@ -110,8 +110,11 @@ __device__ __forceinline__ void warp_copy_out(double *__restrict__ dst, const do
 }
 
 // ------------------------------------------------------------------------------------------------
-// Interpreter of the wave schedules (program.h).  `S` is the QP's slice of shared memory, `t` the
-// lane's accumulator.  The three wave kinds are warp-uniform, so the only divergence is predication.
+// Interpreter of the wave schedules (program.h).  `sb` is the 32-bit shared-window address of the
+// QP's slice, `t` the lane's accumulator.  The wave kind is the same in all lanes (decided by a
+// vote, so the branch is uniform); everything inside a wave is predicated, never divergent.
+// Shared memory is addressed explicitly (ld/st.shared with 32-bit addresses): two integer
+// instructions per operand address instead of a generic-pointer computation.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double regularise(double dk) // ldl.c:319-320
 {
@@ -119,63 +122,136 @@ __device__ __forceinline__ double regularise(double dk) // ldl.c:319-320
 	return (sign * dk <= 0.00000000000001) ? sign * 0.0000001 : dk;
 }
 
-__device__ __forceinline__ void exec_wave(const uint2 ins, double &t, double *__restrict__ S)
+__device__ __forceinline__ double lds64(unsigned addr)
 {
-	const unsigned lo = ins.x, hi = ins.y;
+	double v;
+	asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ void sts64(unsigned addr, double v)
+{
+	asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+// One slot of a quotient / ordered-sum super-wave.  Rare (a few dozen per factorisation) and long
+// (an FP64 division is ~20 dependent instructions), so they are real calls, not inlined copies.
+__device__ __noinline__ void quotient_slot(const unsigned lo, const unsigned hi, const unsigned sb)
+{
 	const unsigned M = (1u << INS_ADDR_BITS) - 1u;
-	if (hi & 0xC0000000u) {
-		if (hi & 0x80000000u) { // quotients
-			if (hi & 0x8000u) S[(hi >> 16) & M] = S[lo & M] / S[(lo >> 16) & M];
-		} else {                // ordered sums: t = S[ci]; t -= S[a+i], i ascending
-			const int cnt = (hi & 0x8000u) ? (int)((lo >> 16) & M) : 0;
-			const int most = __reduce_max_sync(0xffffffffu, cnt);
-			const double *src = S + (lo & M);
-			double acc = S[hi & M];
+	// the divisor is a pivot: dynamic regularisation (ldl.c:319-320) applied on use
+	if (hi & 0x8000u) sts64(sb + (((hi >> 16) & M) << 3), lds64(sb + ((lo & M) << 3)) / regularise(lds64(sb + ((hi & M) << 3))));
+}
+
+__device__ __noinline__ void ordered_sum_slot(const unsigned lo, const unsigned hi, const unsigned sb)
+{
+	const unsigned M = (1u << INS_ADDR_BITS) - 1u;
+	const int cnt = (hi & 0x8000u) ? (int)(hi & M) : 0;
+	const int most = __reduce_max_sync(0xffffffffu, cnt);
+	const unsigned a_at = sb + ((lo & M) << 3);
+	double acc = lds64(sb + (((lo >> 16) & M) << 3)); // t = S[ci]; t -= S[a+i], i ascending
 #pragma unroll 4
-			for (int i = 0; i < most; ++i)
-				if (i < cnt) acc = acc - src[i];
-			if (cnt) S[(hi >> 16) & M] = acc;
+	for (int i = 0; i < most; ++i)
+		if (i < cnt) acc = acc - lds64(a_at + 8u * (unsigned)i);
+	if (cnt) sts64(sb + (((hi >> 16) & M) << 3), acc);
+}
+
+// One super-wave: U instruction words per lane, all of the same kind (a vote makes the branch
+// uniform).  In a multiply-subtract super-wave the loads of all U terms are issued before any
+// arithmetic, so their latencies overlap; everything is predicated, nothing diverges.
+template <int U>
+__device__ __forceinline__ void exec_super(const uint2 (&ins)[U], double (&t)[U], const unsigned sb)
+{
+	const unsigned M = (1u << INS_ADDR_BITS) - 1u;
+	if (__any_sync(0xffffffffu, ins[0].y & 0xC0000000u)) {
+		if (__any_sync(0xffffffffu, ins[0].y & 0x80000000u)) {
+#pragma unroll
+			for (int u = 0; u < U; ++u) quotient_slot(ins[u].x, ins[u].y, sb);
+		} else {
+#pragma unroll
+			for (int u = 0; u < U; ++u) ordered_sum_slot(ins[u].x, ins[u].y, sb);
 		}
-	} else {                    // one term of up to 32 chains
-		const double va = S[lo & M], vb = S[(lo >> 16) & M];
-		if (lo & 0x4000u) // FIRST: t = init + (+0.0 | -0.0)
-			t = S[hi & M] + __hiloint2double((int)((lo << 1) & 0x80000000u), 0);
-		double prod = va * vb;
-		prod = __hiloint2double(__double2hiint(prod) ^ (int)((hi << 17) & 0x80000000u), __double2loint(prod)); // ADD: t - (-prod)
-		t = t - prod;
-		if (lo & 0x8000u) // LAST
-			S[(hi >> 16) & M] = (lo & 0x80000000u) ? regularise(t) : t;
+		return;
+	}
+	double va[U], vb[U], vi[U];
+#pragma unroll
+	for (int u = 0; u < U; ++u) {
+		va[u] = lds64(sb + ((ins[u].x & M) << 3));
+		vb[u] = lds64(sb + ((ins[u].y & M) << 3));
+	}
+#pragma unroll
+	for (int u = 0; u < U; ++u) { // FIRST: fetch the initial value
+		vi[u] = 0.0;
+		asm volatile("{\n\t.reg .pred p;\n\t"
+		             "setp.ne.u32 p, %2, 0;\n\t"
+		             "@p ld.shared.f64 %0, [%1];\n\t}"
+		             : "+d"(vi[u])
+		             : "r"(sb + (((ins[u].x >> 16) & M) << 3)), "r"(ins[u].x & 0x4000u));
+	}
+#pragma unroll
+	for (int u = 0; u < U; ++u) {
+		const unsigned lo = ins[u].x;
+		// FIRST: t = S[ci] + (NEGZ ? -0.0 : +0.0);  then t -= (ADD ? -1 : 1) * va*vb
+		if (lo & 0x4000u) t[u] = vi[u] + __hiloint2double((int)((lo << 1) & 0x80000000u), 0);
+		double prod = va[u] * vb[u];
+		prod = __hiloint2double(__double2hiint(prod) ^ (int)(lo & 0x80000000u), __double2loint(prod));
+		t[u] = t[u] - prod;
+	}
+#pragma unroll
+	for (int u = 0; u < U; ++u) // LAST: S[cs] = t
+		asm volatile("{\n\t.reg .pred p;\n\t"
+		             "setp.ne.u32 p, %2, 0;\n\t"
+		             "@p st.shared.f64 [%0], %1;\n\t}" ::"r"(sb + (((ins[u].y >> 16) & M) << 3)), "d"(t[u]), "r"(ins[u].x & 0x8000u)
+		             : "memory");
+}
+
+template <int U>
+__device__ __forceinline__ void load_words(uint2 (&dst)[U], const uint2 *__restrict__ p)
+{
+	if (U == 1) dst[0] = __ldg(p);
+	else {
+#pragma unroll
+		for (int u = 0; u < U; u += 2) {
+			const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p + u));
+			dst[u] = make_uint2(v.x, v.y);
+			dst[u + 1] = make_uint2(v.z, v.w);
+		}
 	}
 }
 
-// Runs waves [first, first + waves) of `prog` (waves is a multiple of PROGRAM_WAVE_PAD == 4).  The
-// next four instruction words of the lane are always in flight (read-only path, L1 resident
-// while the warps of a CTA run the same segment), so the loop never waits for global memory.
-__device__ __forceinline__ void run_segment(const uint2 *__restrict__ prog, int first, int waves, double *__restrict__ S)
+// Runs `waves` super-waves (a multiple of PROGRAM_WAVE_PAD == 3) starting `first` * 32 words into
+// `prog`.  Three super-waves' worth of instruction words are always in flight (read-only path, L1
+// resident while the warps of a CTA run the same segment); the program buffer is padded so the
+// prefetch needs no bounds check.
+template <int U>
+__device__ __forceinline__ void run_segment_w(const uint2 *__restrict__ prog, int first, int waves, const unsigned sb)
 {
-	const uint2 *p = prog + (size_t)first * 32 + lane_id();
-	uint2 b0 = __ldg(p), b1 = __ldg(p + 32), b2 = __ldg(p + 64), b3 = __ldg(p + 96);
-	double t = 0.0;
-	for (int w = 4; w <= waves; w += 4) {
-		const bool more = w < waves;
-		const uint2 *nx = p + (size_t)w * 32;
-		uint2 c = b0;
-		if (more) b0 = __ldg(nx);
-		exec_wave(c, t, S);
+	const uint2 *p = prog + (size_t)first * 32 + lane_id() * U;
+	uint2 A[U], B[U], C[U];
+	load_words<U>(A, p);
+	load_words<U>(B, p + 32 * U);
+	load_words<U>(C, p + 64 * U);
+	double t[U];
+#pragma unroll
+	for (int u = 0; u < U; ++u) t[u] = 0.0;
+	for (int w = 0; w < waves; w += 3) {
+		p += 96 * U;
+		exec_super<U>(A, t, sb);
 		__syncwarp();
-		c = b1;
-		if (more) b1 = __ldg(nx + 32);
-		exec_wave(c, t, S);
+		load_words<U>(A, p);
+		exec_super<U>(B, t, sb);
 		__syncwarp();
-		c = b2;
-		if (more) b2 = __ldg(nx + 64);
-		exec_wave(c, t, S);
+		load_words<U>(B, p + 32 * U);
+		exec_super<U>(C, t, sb);
 		__syncwarp();
-		c = b3;
-		if (more) b3 = __ldg(nx + 96);
-		exec_wave(c, t, S);
-		__syncwarp();
+		load_words<U>(C, p + 64 * U);
 	}
+}
+
+__device__ __forceinline__ void run_segment(const uint2 *__restrict__ prog, int first, int waves, int width, const unsigned sb)
+{
+	if (width == 4) run_segment_w<4>(prog, first, waves, sb);
+	else if (width == 2) run_segment_w<2>(prog, first, waves, sb);
+	else run_segment_w<1>(prog, first, waves, sb);
 }
 
 struct Scalars

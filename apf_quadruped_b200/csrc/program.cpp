@@ -27,7 +27,18 @@ const int INF = 1 << 30;
 const int TEMP_BASE = 1 << 20;  // value ids >= TEMP_BASE are scheduler-allocated temporaries
 const int ALIAS_BASE = 1 << 19; // ids in [ALIAS_BASE, TEMP_BASE): a second value living at a fixed address (solution over rhs)
 const int DIV_COST = 2;         // a quotient wave is about twice as long as a multiply-subtract wave
-const int SUM_MIN_TERMS = 3;    // backward-sweep columns at least this long use products + ordered sum
+const int SUM_MIN_TERMS = 3;
+// Width of a super-wave in warp-widths: a lane executes `width` independent terms between two
+// __syncwarp()s, so the shared-memory and FP64 latencies of one term hide behind the others.  The
+// factorisation has the parallelism for 4; the triangular solves are critical-path bound.
+static int env_width(const char *name, int dflt)
+{
+	const char *v = getenv(name);
+	const int w = v ? atoi(v) : dflt;
+	return (w == 1 || w == 2 || w == 4) ? w : dflt;
+}
+static const int FACTOR_WIDTH = env_width("QPB_FACTOR_WIDTH", 4);
+static const int SOLVE_WIDTH = env_width("QPB_SOLVE_WIDTH", 2);    // backward-sweep columns at least this long use products + ordered sum
 
 int sum_cost(int count) { return 2 + count / 8; }
 
@@ -71,7 +82,7 @@ struct Issue
 struct Wave
 {
 	int type = 0; // 0 multiply-subtract, 1 quotient, 2 ordered sum
-	std::array<Issue, 32> lane;
+	std::vector<Issue> lane; // 32 * width virtual lanes: lane l, slot u -> index u * 32 + l
 };
 
 struct Builder
@@ -136,7 +147,7 @@ struct ValueTable
 // SUSPENDED (its accumulator is stored to a scratch double in the slot of its last issued term and
 // reloaded, exactly, by whichever lane resumes it), so no set of waiting chains can block the warp.
 // Returns false on an internal inconsistency (never expected).
-bool schedule(Builder &B, int zero_addr, std::vector<Wave> &waves, SegmentStats &st, std::vector<int> &temp_slot, int &temp_count)
+bool schedule(Builder &B, int NL, int zero_addr, std::vector<Wave> &waves, SegmentStats &st, std::vector<int> &temp_slot, int &temp_count)
 {
 	// ---- priorities: longest path to the end, in waves ---------------------------------------------
 	ValueTable H(B, 0);
@@ -177,8 +188,8 @@ bool schedule(Builder &B, int zero_addr, std::vector<Wave> &waves, SegmentStats 
 	for (size_t i = 0; i < pend_unit.size(); ++i) pend_unit[i] = (int)i;
 	size_t remaining = B.chains.size() + B.units.size();
 
-	int lane_chain[32];
-	for (int l = 0; l < 32; ++l) lane_chain[l] = -1;
+	std::vector<int> lane_chain(NL);
+	for (int l = 0; l < NL; ++l) lane_chain[l] = -1;
 
 	st = SegmentStats();
 	st.chains = (int64_t)B.chains.size();
@@ -212,7 +223,7 @@ bool schedule(Builder &B, int zero_addr, std::vector<Wave> &waves, SegmentStats 
 				ready_unit[k].push_back(d);
 				pu[k] = std::max(pu[k], B.units[d].prio);
 			}
-		for (int l = 0; l < 32; ++l) {
+		for (int l = 0; l < NL; ++l) {
 			if (lane_chain[l] < 0) { ++nfree; continue; }
 			any_cont = true;
 			pm = std::max(pm, chain_prio(B.chains[lane_chain[l]]));
@@ -233,18 +244,19 @@ bool schedule(Builder &B, int zero_addr, std::vector<Wave> &waves, SegmentStats 
 		if (!can_mul && ready_unit[0].empty() && ready_unit[1].empty()) return false;
 
 		Wave W;
-		for (int l = 0; l < 32; ++l) { W.lane[l].a = W.lane[l].b = W.lane[l].ci = W.lane[l].cs = zero_addr; }
+		W.lane.assign(NL, Issue());
+		for (int l = 0; l < NL; ++l) { W.lane[l].a = W.lane[l].b = W.lane[l].ci = W.lane[l].cs = zero_addr; }
 		int type = 0;
 		{
 			int best = can_mul ? pm : -1;
 			for (int k = 0; k < 2; ++k)
-				if (!ready_unit[k].empty() && (pu[k] > best || ready_unit[k].size() >= (k == 1 ? 16u : 32u))) { best = std::max(best, pu[k]); type = k + 1; }
+				if (!ready_unit[k].empty() && (pu[k] > best || ready_unit[k].size() >= (size_t)(k == 1 ? NL / 2 : NL))) { best = std::max(best, pu[k]); type = k + 1; }
 		}
 		W.type = type;
 		if (type != 0) {
 			std::vector<int> &ready = ready_unit[type - 1];
 			std::stable_sort(ready.begin(), ready.end(), [&](int x, int y) { return B.units[x].prio > B.units[y].prio; });
-			const size_t take = std::min<size_t>(32, ready.size());
+			const size_t take = std::min<size_t>(NL, ready.size());
 			std::vector<char> gone(B.units.size(), 0);
 			for (size_t l = 0; l < take; ++l) {
 				const Unit &d = B.units[ready[l]];
@@ -266,7 +278,7 @@ bool schedule(Builder &B, int zero_addr, std::vector<Wave> &waves, SegmentStats 
 			pend_unit.erase(std::remove_if(pend_unit.begin(), pend_unit.end(), [&](int d) { return gone[d]; }), pend_unit.end());
 			++(type == 1 ? st.div_waves : st.sum_waves);
 		} else {
-			bool fresh[32] = {false}; // lane freed in this wave: its slot is taken
+			std::vector<char> fresh(NL, 0); // lane freed in this wave: its slot is taken
 			auto issue_term = [&](int l, Chain &c) {
 				Issue &is = W.lane[l];
 				is.kind = 1; is.add = c.add;
@@ -287,12 +299,12 @@ bool schedule(Builder &B, int zero_addr, std::vector<Wave> &waves, SegmentStats 
 					--remaining;
 				}
 			};
-			for (int l = 0; l < 32; ++l)
+			for (int l = 0; l < NL; ++l)
 				if (lane_chain[l] >= 0) issue_term(l, B.chains[lane_chain[l]]);
 			std::stable_sort(cand.begin(), cand.end(), [&](int x, int y) { return chain_prio(B.chains[x]) > chain_prio(B.chains[y]); });
 			size_t next = 0;
 			std::vector<char> gone(B.chains.size(), 0);
-			for (int l = 0; l < 32 && next < cand.size(); ++l) {
+			for (int l = 0; l < NL && next < cand.size(); ++l) {
 				if (lane_chain[l] >= 0 || fresh[l]) continue;
 				const int ci = cand[next++];
 				Chain &c = B.chains[ci];
@@ -307,7 +319,7 @@ bool schedule(Builder &B, int zero_addr, std::vector<Wave> &waves, SegmentStats 
 			}
 			pend_chain.erase(std::remove_if(pend_chain.begin(), pend_chain.end(), [&](int c) { return gone[c]; }), pend_chain.end());
 			// suspend every chain that cannot continue in the next wave
-			for (int l = 0; l < 32; ++l) {
+			for (int l = 0; l < NL; ++l) {
 				if (lane_chain[l] < 0) continue;
 				Chain &c = B.chains[lane_chain[l]];
 				if (A.at(c.terms[c.pos].first) <= wave + 1 && A.at(c.terms[c.pos].second) <= wave + 1) continue;
@@ -367,7 +379,7 @@ bool schedule(Builder &B, int zero_addr, std::vector<Wave> &waves, SegmentStats 
 		for (size_t w = 0; w < live.size(); ++w) if (live[w] > mx) { mx = live[w]; at = (int)w; }
 		fprintf(stderr, "[sched] waves %zu temps allocated %d, max live %d at wave %d\n", waves.size(), temp_count, mx, at);
 		std::string types;
-		for (const Wave &W : waves) { int act = 0; for (int l = 0; l < 32; ++l) act += W.lane[l].kind != 0; types += (W.type == 0 ? "m" : W.type == 1 ? "D" : "S"); types += std::to_string(act) + " "; }
+		for (const Wave &W : waves) { int act = 0; for (int l = 0; l < NL; ++l) act += W.lane[l].kind != 0; types += (W.type == 0 ? "m" : W.type == 1 ? "D" : "S"); types += std::to_string(act) + " "; }
 		fprintf(stderr, "[sched] %s\n", types.c_str());
 	}
 	st.waves = (int)waves.size();
@@ -377,32 +389,37 @@ bool schedule(Builder &B, int zero_addr, std::vector<Wave> &waves, SegmentStats 
 uint64_t encode(const Issue &is, int type, int tbase, const std::vector<int> &temp_slot, const std::vector<int> &alias_phys)
 {
 	auto addr = [&](int id) -> uint64_t { return (uint64_t)(id >= TEMP_BASE ? tbase + temp_slot[id - TEMP_BASE] : id >= ALIAS_BASE ? alias_phys[id - ALIAS_BASE] : id); };
+	auto pack = [](uint64_t a, uint64_t ci, uint64_t b, uint64_t cs) { return a | (ci << 16) | (b << 32) | (cs << 48); };
 	if (type != 0) {
 		uint64_t w = type == 1 ? INS_DIVWAVE : INS_SUMWAVE;
-		if (is.kind == 2) w |= INS_ACTIVE | addr(is.a) | (addr(is.b) << 16) | (addr(is.cs) << 48);
-		else if (is.kind == 3) w |= INS_ACTIVE | addr(is.a) | ((uint64_t)is.b << 16) | (addr(is.ci) << 32) | (addr(is.cs) << 48);
-		else w |= addr(is.a) | (addr(is.a) << 16) | (addr(is.a) << 32) | (addr(is.a) << 48);
+		if (is.kind == 2) w |= INS_ACTIVE | pack(addr(is.a), addr(is.a), addr(is.b), addr(is.cs));
+		else if (is.kind == 3) w |= INS_ACTIVE | pack(addr(is.a), addr(is.ci), (uint64_t)is.b, addr(is.cs));
+		else w |= pack(addr(is.a), addr(is.a), type == 1 ? addr(is.a) : 0, addr(is.a));
 		return w;
 	}
-	uint64_t w = addr(is.a) | (addr(is.b) << 16) | (addr(is.ci) << 32) | (addr(is.cs) << 48);
+	uint64_t w = pack(addr(is.a), addr(is.ci), addr(is.b), addr(is.cs));
 	if (is.first) w |= INS_FIRST;
 	if (is.last) w |= INS_LAST;
 	if (is.negz) w |= INS_NEGZ;
-	if (is.reg) w |= INS_REG;
 	if (is.add) w |= INS_ADD;
 	return w;
 }
 
-void emit(const std::vector<Wave> &waves, int zero_addr, int tbase, const std::vector<int> &temp_slot, const std::vector<int> &alias_phys, std::vector<uint64_t> &words, Segment &seg)
+// Words are stored [super-wave][lane][slot]: a lane reads its `width` instruction words with one load.
+void emit(const std::vector<Wave> &waves, int width, int zero_addr, int tbase, const std::vector<int> &temp_slot, const std::vector<int> &alias_phys, std::vector<uint64_t> &words, Segment &seg)
 {
 	seg.first = (int32_t)(words.size() / 32);
+	seg.width = width;
 	for (const Wave &W : waves)
-		for (int l = 0; l < 32; ++l) words.push_back(encode(W.lane[l], W.type, tbase, temp_slot, alias_phys));
+		for (int l = 0; l < 32; ++l)
+			for (int u = 0; u < width; ++u) words.push_back(encode(W.lane[u * 32 + l], W.type, tbase, temp_slot, alias_phys));
 	Issue idle;
 	idle.a = idle.b = idle.ci = idle.cs = zero_addr;
-	while ((words.size() / 32 - seg.first) % PROGRAM_WAVE_PAD != 0)
-		for (int l = 0; l < 32; ++l) words.push_back(encode(idle, 0, tbase, temp_slot, alias_phys));
-	seg.waves = (int32_t)(words.size() / 32 - seg.first);
+	seg.waves = (int32_t)waves.size();
+	while (seg.waves % PROGRAM_WAVE_PAD != 0) {
+		for (int l = 0; l < 32 * width; ++l) words.push_back(encode(idle, 0, tbase, temp_slot, alias_phys));
+		++seg.waves;
+	}
 }
 
 int even(long v) { return (int)((v + 1) & ~1L); }
@@ -475,7 +492,7 @@ bool build_program(const Plan &pl, Program &prog)
 	std::vector<Wave> fwaves;
 	std::vector<int> ftemp_slot;
 	int ftemps = 0;
-	if (!schedule(F, L.zero, fwaves, prog.factor.stats, ftemp_slot, ftemps)) { prog.error = "factor schedule failed"; return false; }
+	if (!schedule(F, 32 * FACTOR_WIDTH, L.zero, fwaves, prog.factor.stats, ftemp_slot, ftemps)) { prog.error = "factor schedule failed"; return false; }
 
 	// The solve's work vectors wf, wd sit at the start of T and its scheduler temporaries behind them;
 	// T is sized for the larger of the two programs.  The schedule does not depend on addresses, so
@@ -557,12 +574,17 @@ bool build_program(const Plan &pl, Program &prog)
 		}
 	}
 	const int before = stemps;
-	if (!schedule(S, L.zero, swaves, prog.solve.stats, stemp_slot, stemps)) { prog.error = "solve schedule failed"; return false; }
+	if (!schedule(S, 32 * SOLVE_WIDTH, L.zero, swaves, prog.solve.stats, stemp_slot, stemps)) { prog.error = "solve schedule failed"; return false; }
 	if (pass == 1 && stemps != before) { prog.error = "solve schedule is not reproducible"; return false; }
 	}
 
-	emit(fwaves, L.zero, L.T, ftemp_slot, F.alias_phys, prog.words, prog.factor);
-	emit(swaves, L.zero, L.T + 2 * N, stemp_slot, S.alias_phys, prog.words, prog.solve);
+	emit(fwaves, FACTOR_WIDTH, L.zero, L.T, ftemp_slot, F.alias_phys, prog.words, prog.factor);
+	emit(swaves, SOLVE_WIDTH, L.zero, L.T + 2 * N, stemp_slot, S.alias_phys, prog.words, prog.solve);
+	{ // the kernel prefetches PROGRAM_WAVE_PAD waves ahead without a bounds check
+		Issue idle;
+		idle.a = idle.b = idle.ci = idle.cs = L.zero;
+		for (int i = 0; i < PROGRAM_WAVE_PAD * 32 * std::max(FACTOR_WIDTH, SOLVE_WIDTH); ++i) prog.words.push_back(encode(idle, 0, L.T, ftemp_slot, F.alias_phys));
+	}
 	prog.ok = true;
 	return true;
 }

@@ -45,24 +45,27 @@ struct SliceLayout
 };
 
 // Instruction word, one per lane per wave (64 bit = four 16-bit fields, index in the low 14 bits):
-//   field 0: a   | FIRST << 14 | LAST << 15
-//   field 1: b   | NEGZ  << 14 | REG  << 15
-//   field 2: ci  | ADD   << 14 | ACTIVE << 15
+//   field 0: a   | FIRST << 14 | LAST << 15          (low half of the low word)
+//   field 1: ci  | NEGZ  << 14 | ADD  << 15
+//   field 2: b   |      0      | ACTIVE << 15        (low half of the high word)
 //   field 3: cs  | SUMWAVE << 14 | DIVWAVE << 15
 // multiply-subtract wave:  if FIRST: t = S[ci] + (NEGZ ? -0.0 : +0.0);   t = t -/+ S[a]*S[b];
-//                          if LAST:  S[cs] = REG ? regularise(t) : t
-// quotient wave (DIVWAVE set in every lane): if ACTIVE: S[cs] = S[a] / S[b]
+//                          if LAST:  S[cs] = t
+// quotient wave (DIVWAVE set in every lane): if ACTIVE: S[cs] = S[a] / regularise(S[b])
+//   -- every divisor of the factorisation and of the solves is a pivot D[i]; the dynamic
+//   regularisation of ldl.c:319-320 is idempotent, so it is applied where D is USED and the
+//   chains store the raw pivot (the stand-alone factor kernel regularises D on the way out).
 // ordered-sum wave (SUMWAVE set in every lane): if ACTIVE: t = S[ci]; for i < b: t = t - S[a+i]; S[cs] = t
-//   (field 1 holds the COUNT b, not an address)
+//   (field 2 holds the COUNT b, not an address)
 enum : uint64_t
 {
 	INS_FIRST = 1ull << 14, INS_LAST = 1ull << 15,
-	INS_NEGZ = 1ull << 30, INS_REG = 1ull << 31,
-	INS_ADD = 1ull << 46, INS_ACTIVE = 1ull << 47,
+	INS_NEGZ = 1ull << 30, INS_ADD = 1ull << 31,
+	INS_ACTIVE = 1ull << 47,
 	INS_SUMWAVE = 1ull << 62, INS_DIVWAVE = 1ull << 63
 };
 static const int INS_ADDR_BITS = 14;
-static const int PROGRAM_WAVE_PAD = 4; // segments are padded to a multiple of this many waves (kernel prefetch depth)
+static const int PROGRAM_WAVE_PAD = 3; // segments are padded to a multiple of this many super-waves (kernel prefetch depth)
 
 struct SegmentStats
 {
@@ -74,15 +77,16 @@ struct SegmentStats
 
 struct Segment
 {
-	int32_t first = 0; // first wave (index into Program::words / 32)
-	int32_t waves = 0; // padded wave count
+	int32_t first = 0; // offset of the segment in Program::words, in units of 32 words
+	int32_t waves = 0; // padded super-wave count
+	int32_t width = 1; // instruction words per lane per super-wave (1, 2 or 4)
 	SegmentStats stats;
 };
 
 struct Program
 {
 	SliceLayout lay;
-	std::vector<uint64_t> words; // [wave][32]
+	std::vector<uint64_t> words; // per segment [super-wave][lane][slot]
 	Segment factor, solve;
 	bool ok = false;
 	std::string error;

@@ -165,7 +165,7 @@ class Plan:
             "program_ok": 8, "slice_doubles": 9, "program_words": 10}
     SEGMENT = {"factor": 32, "solve": 48}
     SEGMENT_STATS = ["waves", "mul_waves", "div_waves", "terms", "divs", "chains", "lane_slots", "temps", "sum_waves",
-                     "sums", "suspensions", "first"]
+                     "sums", "suspensions", "first", "width"]
     LAYOUT = ["zero", "V", "c", "h", "b", "zd", "Lx", "D", "T", "rhs", "x", "y", "z", "s", "r", "lam", "ds", "dz", "dsl",
               "total", "tsize"]
 
@@ -200,13 +200,17 @@ class Plan:
         assert cnt == len(self.LAYOUT)
         return {n: int(buf[i]) for i, n in enumerate(self.LAYOUT)}
 
-    def program(self) -> np.ndarray:
-        """The instruction words, shape (waves, 32), uint64."""
+    def program(self, which: str | None = None) -> np.ndarray:
+        """The instruction words (uint64): all of them, flat, or one schedule as an array of shape
+        (super-waves, 32 lanes, width)."""
         cnt = C.c_long()
         ptr = lib().QPB_PLAN_PROGRAM(self.handle, C.byref(cnt))
-        if cnt.value == 0:
-            return np.zeros((0, 32), dtype=np.uint64)
-        return np.ctypeslib.as_array(ptr, shape=(cnt.value,)).copy().reshape(-1, 32)
+        words = np.ctypeslib.as_array(ptr, shape=(cnt.value,)).copy() if cnt.value else np.zeros(0, dtype=np.uint64)
+        if which is None:
+            return words
+        seg = self.segment(which)
+        lo = seg["first"] * 32
+        return words[lo:lo + seg["waves"] * 32 * seg["width"]].reshape(seg["waves"], 32, seg["width"])
 
     def close(self):
         if self.handle:
