@@ -10,7 +10,7 @@ SRC      := apf_quadruped_b200/csrc
 OBJ      := build/obj
 LIB      := apf_quadruped_b200/lib/libqpswift_b200.so
 
-HOST_SRCS := $(SRC)/amd_order.cpp $(SRC)/symbolic.cpp $(SRC)/program.cpp $(SRC)/capi_plan.cpp $(SRC)/capi_qp.cpp
+HOST_SRCS := $(SRC)/amd_order.cpp $(SRC)/symbolic.cpp $(SRC)/program.cpp $(SRC)/stream_program.cpp $(SRC)/capi_plan.cpp $(SRC)/capi_qp.cpp
 HOST_OBJS := $(patsubst $(SRC)/%.cpp,$(OBJ)/%.o,$(HOST_SRCS))
 CU_SRCS   := $(SRC)/batch.cu
 CU_OBJS   := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(CU_SRCS))

@@ -13,9 +13,11 @@
 
 #include "capi_internal.h"
 #include "kernels.cuh"
+#include "stream.cuh"
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -234,6 +236,14 @@ struct QPBatch
 	int *d_counter = nullptr;
 	ProgramView pview;
 	int max_warps = 1;      // slices of shared memory that fit next to each other in one CTA
+	// throughput kernel (stream.cuh)
+	StreamProgram sprog;
+	uint2 *d_stream = nullptr;
+	double *d_workspace = nullptr;
+	StreamView sview;
+	int stream_warps = 0;   // warps per CTA (0: the pattern cannot use the throughput kernel)
+	long stream_slots = 0;  // warps in flight on the device = tiles of 32 slices in the workspace
+	long stream_min = 0;    // smallest batch that goes to the throughput kernel
 	size_t smem_limit = 0;
 	// device staging for the host-pointer entry point
 	double *d_in[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -244,6 +254,7 @@ struct QPBatch
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	double last_kernel_ms = 0.0;
 	long last_launches = 0;
+	int last_kernel = 0; // 0 latency kernel (one QP per warp), 1 throughput kernel (one QP per thread)
 	std::mutex lock;
 };
 
@@ -275,6 +286,26 @@ static int batch_alloc(QPBatch *B)
 	B->pview.f_first = pg.factor.first; B->pview.f_waves = pg.factor.waves; B->pview.f_width = pg.factor.width;
 	B->pview.s_first = pg.solve.first; B->pview.s_waves = pg.solve.waves; B->pview.s_width = pg.solve.width;
 	CUDA_TRY(cudaMalloc(&B->d_counter, 64 * sizeof(int)));
+	// ---- throughput kernel: one thread per QP, slices interleaved in an HBM workspace ---------------
+	if (B->sprog.ok) {
+		const size_t window = (size_t)B->sprog.lay.scratch * 32 * sizeof(double); // shared memory per warp
+		long cap = getenv("QPB_STREAM_WARPS") ? atol(getenv("QPB_STREAM_WARPS")) : STREAM_MAX_WARPS;
+		if (cap > STREAM_MAX_WARPS) cap = STREAM_MAX_WARPS;
+		B->stream_warps = (int)std::min<size_t>((size_t)std::max(cap, 1L), B->smem_limit / window);
+	}
+	if (B->stream_warps > 0) {
+		const StreamProgram &sp = B->sprog;
+		CUDA_TRY(cudaFuncSetAttribute(qp_solve_stream_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
+		CUDA_TRY(cudaFuncSetAttribute(qp_solve_stream_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
+		CUDA_TRY(cudaMalloc(&B->d_stream, sp.words.size() * sizeof(uint64_t)));
+		CUDA_TRY(cudaMemcpy(B->d_stream, sp.words.data(), sp.words.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+		B->sview.words = B->d_stream;
+		for (int s = 0; s < SSEG_COUNT; ++s) { B->sview.first[s] = sp.seg[s].first; B->sview.groups[s] = sp.seg[s].groups; }
+		const long full = (long)B->sm_count * B->stream_warps;
+		B->stream_slots = std::min(full, (B->capacity + 31) / 32);
+		B->stream_min = getenv("QPB_STREAM_MIN") ? atol(getenv("QPB_STREAM_MIN")) : 2048;
+		if (B->capacity >= B->stream_min) CUDA_TRY(cudaMalloc(&B->d_workspace, (size_t)B->stream_slots * sp.lay.total * 32 * sizeof(double)));
+	}
 	CUDA_TRY(cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking));
 	CUDA_TRY(cudaEventCreate(&B->ev0));
 	CUDA_TRY(cudaEventCreate(&B->ev1));
@@ -302,6 +333,26 @@ static int batch_alloc_staging(QPBatch *B)
 	return 0;
 }
 
+// Large batches: one thread per QP (stream.cuh).  One CTA per SM, stream_warps warps each.
+static int launch_stream(QPBatch *B, const BatchIO &io, const SolveParams &prm, cudaStream_t st)
+{
+	const StreamProgram &sp = B->sprog;
+	long slots = std::min(B->stream_slots, ((long)io.count + 31) / 32);
+	const long warps = std::min<long>(B->stream_warps, std::max(1L, (slots + B->sm_count - 1) / B->sm_count));
+	const long grid = (slots + warps - 1) / warps;
+	const size_t smem = (size_t)warps * sp.lay.scratch * 32 * sizeof(double);
+	StreamDims dm;
+	dm.n = (int)B->plan.n; dm.m = (int)B->plan.m; dm.p = (int)B->plan.p; dm.N = (int)B->plan.N;
+	dm.nnzP = (int)B->plan.nnzP; dm.nnzA = (int)B->plan.nnzA; dm.nnzG = (int)B->plan.nnzG;
+	if (sp.group == 4) qp_solve_stream_kernel<4><<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->sview, sp.lay, dm, io, prm, B->d_workspace, (int)slots, B->d_counter);
+	else if (sp.group == 8) qp_solve_stream_kernel<8><<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->sview, sp.lay, dm, io, prm, B->d_workspace, (int)slots, B->d_counter);
+	else return fail(QPB_E_ARG, "stream program: unsupported group size", cudaSuccess);
+	CUDA_TRY(cudaGetLastError());
+	B->last_launches = 1;
+	B->last_kernel = 1;
+	return 0;
+}
+
 static int launch_fused(QPBatch *B, const BatchIO &io, const settings *opts, cudaStream_t st)
 {
 	SolveParams prm;
@@ -311,6 +362,8 @@ static int launch_fused(QPBatch *B, const BatchIO &io, const settings *opts, cud
 	prm.sigma0 = opts->sigma;
 	prm.sigma_d = B->sigma_d;
 	CUDA_TRY(cudaMemsetAsync(B->d_counter, 0, sizeof(int), st));
+	if (B->d_workspace && io.count >= B->stream_min) return launch_stream(B, io, prm, st);
+	B->last_kernel = 0;
 	// one persistent CTA per SM; small batches spread over the SMs with fewer warps per CTA
 	long warps = (io.count + B->sm_count - 1) / B->sm_count;
 	if (warps > B->max_warps) warps = B->max_warps;
@@ -343,6 +396,7 @@ QPBatch *QPB_BATCH_CREATE(const QPBPlan *plan, qp_real sigma_d, qp_int capacity,
 	if (!plan->program.ok) { g_last_error = "QPB_BATCH_CREATE: " + plan->program.error; return nullptr; }
 	B->plan = plan->plan;
 	B->program = plan->program;
+	B->sprog = plan->stream;
 	B->sigma_d = sigma_d;
 	B->capacity = capacity;
 	B->device = device;
@@ -365,6 +419,8 @@ void QP_CLEANUP_BATCH(QPBatch *B)
 	cudaSetDevice(B->device);
 	cudaFree(B->d_plan);
 	cudaFree(B->d_prog);
+	cudaFree(B->d_stream);
+	cudaFree(B->d_workspace);
 	cudaFree(B->d_counter);
 	for (int i = 0; i < 6; ++i) cudaFree(B->d_in[i]);
 	cudaFree(B->d_x); cudaFree(B->d_y); cudaFree(B->d_z); cudaFree(B->d_s);
@@ -441,6 +497,7 @@ qp_int QPB_BATCH_SET_SIGMA_D(QPBatch *B, qp_real sigma_d)
 
 double QPB_BATCH_LAST_KERNEL_MS(const QPBatch *B) { return B ? B->last_kernel_ms : 0.0; }
 qp_int QPB_BATCH_LAST_LAUNCHES(const QPBatch *B) { return B ? B->last_launches : 0; }
+int QPB_BATCH_LAST_KERNEL(const QPBatch *B) { return B ? B->last_kernel : -1; }
 
 // Host access to fval / stat of the last host-pointer solve (used by QP_SOLVE to fill `stats`).
 qp_int QPB_BATCH_READ_STATS(QPBatch *B, qp_int count, qp_real *fval, qp_real *stat)

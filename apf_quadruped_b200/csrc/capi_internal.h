@@ -5,11 +5,13 @@
 #include "qpswift_b200.h"
 #include "plan.h"
 #include "program.h"
+#include "stream_program.h"
 
 struct QPBPlan
 {
 	qpb::Plan plan;
-	qpb::Program program; // factor / solve schedules compiled from the plan (program.h)
+	qpb::Program program; // factor / solve schedules compiled from the plan (program.h): latency kernel
+	qpb::StreamProgram stream; // micro-programs of the throughput kernel (stream_program.h)
 };
 
 // build_plan + build_program; returns plan.valid && program.ok

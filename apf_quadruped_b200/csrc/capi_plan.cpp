@@ -2,12 +2,17 @@
 
 #include "capi_internal.h"
 
+#include <cstdlib>
+#include <vector>
+
 using namespace qpb;
 
 bool qpb_build(QPBPlan &h, qp_int n, qp_int m, qp_int p, const qp_int *Pjc, const qp_int *Pir, const qp_int *Ajc, const qp_int *Air, const qp_int *Gjc, const qp_int *Gir, const qp_int *Permut)
 {
 	if (!build_plan(h.plan, n, m, p, Pjc, Pir, Ajc, Air, Gjc, Gir, Permut)) return false;
-	return build_program(h.plan, h.program);
+	const bool ok = build_program(h.plan, h.program);
+	const char *g = getenv("QPB_STREAM_GROUP"); // experiments: micro-ops per group (4 or 8)
+	return build_stream_program(h.plan, h.stream, g && atoi(g) == 4 ? 4 : 8) && ok;
 }
 
 extern "C" {
@@ -94,6 +99,28 @@ qp_int QPB_PLAN_LAYOUT(const QPBPlan *h, int *out, int capacity)
 	const int32_t *src = reinterpret_cast<const int32_t *>(&h->program.lay);
 	for (int i = 0; i < count && i < capacity; ++i) out[i] = src[i];
 	return count;
+}
+
+const unsigned long long *QPB_PLAN_STREAM(const QPBPlan *h, qp_int *words)
+{
+	if (words) *words = (qp_int)h->stream.words.size();
+	return reinterpret_cast<const unsigned long long *>(h->stream.words.data());
+}
+
+qp_int QPB_PLAN_STREAM_INFO(const QPBPlan *h, long long *out, int capacity)
+{
+	std::vector<long long> v;
+	const int32_t *lay = reinterpret_cast<const int32_t *>(&h->stream.lay);
+	for (size_t i = 0; i < sizeof(StreamLayout) / sizeof(int32_t); ++i) v.push_back(lay[i]);
+	v.push_back(h->stream.ok ? 1 : 0);
+	v.push_back(h->stream.group);
+	for (int s = 0; s < SSEG_COUNT; ++s) {
+		const StreamSegment &g = h->stream.seg[s];
+		const long long row[10] = {g.first, g.groups, g.ops, g.terms, g.divs, g.late, g.hbm_loads, g.hbm_stores, g.nops, g.slow_groups};
+		v.insert(v.end(), row, row + 10);
+	}
+	for (size_t i = 0; i < v.size() && (int)i < capacity; ++i) out[i] = v[i];
+	return (qp_int)v.size();
 }
 
 qp_int QPB_AMD_ORDER(qp_int n, const qp_int *Ap, const qp_int *Ai, qp_int *Perm)

@@ -1,0 +1,392 @@
+// Throughput kernel of the batched interior-point solver (sm_100a, FP64): ONE THREAD PER QP.
+//
+// The 32 lanes of a warp run 32 QPs of the same sparsity pattern in lock step.  A QP's whole
+// working set (value row, factor, iterate, residuals: StreamLayout) is a slice of HBM interleaved
+// with the slices of the other 31 lanes -- element e of lane l lives at base + e*32 + l -- so every
+// load and store of the warp is one fully used 256-byte line, whatever the sparsity pattern asks for.
+// The factorisation, the triangular solves and the sparse residual products are micro-programs
+// compiled per pattern on the host (stream_program.h) and interpreted here: the warp executes a
+// GROUP of micro-ops at a time, first issuing every HBM load of the group (they are independent of
+// the group's arithmetic by construction), then running the arithmetic in the reference's order with
+// the two accumulators in registers and the row-local work vector in shared memory.  HBM latency is
+// covered by the loads in flight per warp (up to 2 per micro-op) times the warps per SM, not by
+// occupancy alone.
+//
+// Arithmetic contract: each thread performs exactly the reference's IEEE-754 binary64 operations in
+// the reference's order (file compiled with -fmad=false), so x, y, z, s, the iteration count and the
+// exit flag are bit-identical with reference qpSWIFT, and independent of the batch composition.
+//
+// Lanes are scheduled individually: a lane whose QP has left the interior-point loop writes it
+// back and pulls the next QP of the batch from an atomic counter; the new QP's initial point
+// (kkt_initialize) is one more factor + solve of the same programs, so lanes at different iteration
+// counts never wait for one another.
+//
+// Reference routines restated (dogbot_controller/src/qpSWIFT/): see kernels.cuh for the list; the
+// elementwise steps below follow Auxilary.c:205-393, 638-646, 879-892, 992-1089 and qpSWIFT.c:473-644.
+#pragma once
+
+#include "kernels.cuh"
+#include "stream_program.h"
+
+namespace qpb {
+
+struct StreamView
+{
+	const uint2 *words;
+	int first[SSEG_COUNT], groups[SSEG_COUNT];
+};
+
+struct StreamDims
+{
+	int n, m, p, N, nnzP, nnzA, nnzG;
+};
+
+#ifdef __CUDACC__
+
+// Interpreter.  g: the lane's slice (element e at g[e << 5]); sb: the lane's window of shared memory
+// (element e at sb + (e << 8)).  G micro-ops per group.  Software pipeline, per iteration:
+//   request the HBM operands of group i+1   (words fetched one iteration ago)
+//   fetch the words of group i+2
+//   execute group i                          (operands requested one iteration ago)
+// so two groups of operands (2G or 4G lines of 256 bytes per warp) are in flight while a group runs.
+// A FAST group is executed without a single branch (flags become predicates and selects), a SLOW
+// group micro-op by micro-op; the words are the same in all lanes, a REDUX puts them into uniform
+// registers so that the dispatch costs no divergence handling.
+// GG = false: factor / solve programs (second operand in the shared window); GG = true: residual
+// programs (second operand prefetched from HBM as well, results to HBM).
+// __noinline__: one copy serves all call sites (instruction cache).
+
+// A load the compiler may neither delay to its first use nor move into a branch: the requests of a
+// group have to be in flight together.
+__device__ __forceinline__ double ldg_now(const double *p)
+{
+	double v;
+	asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+	return v;
+}
+
+template <int G>
+__device__ __forceinline__ void fetch_words(uint2 (&dst)[G], const uint2 *__restrict__ prog)
+{
+#pragma unroll
+	for (int u = 0; u < G; u += 2) {
+		const uint4 v = __ldg(reinterpret_cast<const uint4 *>(prog + u));
+		dst[u] = make_uint2(v.x, v.y);
+		dst[u + 1] = make_uint2(v.z, v.w);
+	}
+}
+
+template <int G, bool GG>
+__device__ __forceinline__ void request(const uint2 (&w)[G], double (&p1)[G], double (&p2)[GG ? G : 1], const double *g)
+{
+#pragma unroll
+	for (int u = 0; u < G; ++u) {
+		p1[u] = ldg_now(g + ((w[u].x & 0xffffu) << 5));
+		if (GG) p2[u] = ldg_now(g + ((w[u].x >> 16) << 5));
+	}
+}
+
+#define HI(flag) ((unsigned)((flag) >> 32))
+
+template <int G, bool GG>
+__device__ __noinline__ void run_stream(const uint2 *__restrict__ prog, const int ngroups, double *g, const unsigned sb)
+{
+	uint2 cur[G], nxt[G], far[G];
+	double p1[G], p2[GG ? G : 1], q1[G], q2[GG ? G : 1];
+	fetch_words<G>(cur, prog);
+	fetch_words<G>(nxt, prog + G);
+	request<G, GG>(cur, p1, p2, g);
+	prog += 2 * G;
+	double t = 0.0, d = 0.0;
+	for (int grp = 0; grp < ngroups; ++grp) {
+		request<G, GG>(nxt, q1, q2, g); // beyond the last group: the padding words point at a constant
+		fetch_words<G>(far, prog);
+		prog += G;
+		if (!__reduce_or_sync(0xffffffffu, cur[0].y & HI(SF_SLOW))) {
+#pragma unroll
+			for (int u = 0; u < G; ++u) {
+				const unsigned lo = cur[u].x, hi = cur[u].y;
+				const double s = GG ? p2[u] : lds64(sb + ((lo >> 16) << 8));
+				const double base = (hi & HI(SF_FIRSTZ)) ? 0.0 : t;
+				const double r = base - p1[u] * s;
+				t = (hi & HI(SF_INIT)) ? p1[u] : r;
+				if (GG) {
+					if (hi & HI(SF_ST_HBM)) g[(hi & 0xffffu) << 5] = t;
+				} else {
+					if (hi & HI(SF_ST_SHARED)) sts64(sb + ((hi & 0xffffu) << 8), t);
+				}
+			}
+		} else {
+#pragma unroll 1
+			for (int u = 0; u < G; ++u) {
+				// (rolled: the words of slot u are selected below; slow groups are a small share of the work)
+				uint2 w = cur[0];
+				double P = p1[0], S2 = GG ? p2[0] : 0.0;
+#pragma unroll
+				for (int v = 1; v < G; ++v)
+					if (v == u) { w = cur[v]; P = p1[v]; if (GG) S2 = p2[v]; }
+				const unsigned lo = __reduce_or_sync(0xffffffffu, w.x), hi = __reduce_or_sync(0xffffffffu, w.y);
+				const unsigned op = (hi >> 16) & 15u;
+				if (hi & HI(SF_LATE1)) P = g[(lo & 0xffffu) << 5];
+				double S = 0.0;
+				if (GG) S = (hi & HI(SF_LATE2)) ? g[(lo >> 16) << 5] : S2;
+				else if (op == SOP_TERM || op == SOP_DIVACC || op == SOP_DIV || op == SOP_LOADS) S = lds64(sb + ((lo >> 16) << 8));
+				if (op == SOP_TERM) {
+					const double base = (hi & HI(SF_FIRSTZ)) ? 0.0 : t;
+					const double r = base - P * S;
+					t = (hi & HI(SF_INIT)) ? P : r;
+				} else if (op == SOP_DIVACC) {
+					t = S / P;
+					d = d - t * S;
+				} else if (op == SOP_DIV) t = S / P;
+				else if (op == SOP_INITD) d = P;
+				else if (op == SOP_ENDD) t = regularise(d);
+				else if (op == SOP_LOADS) t = S;
+				if (hi & HI(SF_ST_HBM)) g[(hi & 0xffffu) << 5] = t;
+				if (!GG && (hi & HI(SF_ST_SHARED))) sts64(sb + ((hi & 0xffffu) << 8), t);
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < G; ++u) {
+			cur[u] = nxt[u]; nxt[u] = far[u];
+			p1[u] = q1[u];
+			if (GG) p2[u] = q2[u];
+		}
+	}
+}
+#undef HI
+
+// Sequential inner product sum_i a[i]*b[i] from 0.0 in ascending order (norm Auxilary.c:430-440,
+// innerproduct 451-462); the loads and products of eight terms are issued together.
+__device__ __forceinline__ double stream_dot(const double *a, const double *b, const int count)
+{
+	double acc = 0.0;
+	for (int i0 = 0; i0 < count; i0 += 8) {
+		double pa[8], pb[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const int i = min(i0 + j, count - 1);
+			pa[j] = a[i << 5];
+			pb[j] = b[i << 5];
+		}
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			if (i0 + j < count) acc += pa[j] * pb[j];
+	}
+	return acc;
+}
+
+enum { SM_IDLE = 0, SM_INIT = 1, SM_PRED = 2, SM_CENT = 3 };
+static const int STREAM_MAX_WARPS = 8;
+static const int STREAM_U = 8; // elements of an elementwise step whose loads are issued together
+
+#define SL(e) g[(unsigned)(e) << 5]
+// for (i < count): LOADS; then BODY, eight elements at a time with all loads first
+#define STREAM_FOR(count, LOADS, BODY)                                 \
+	for (int i0__ = 0; i0__ < (count); i0__ += STREAM_U) {             \
+		_Pragma("unroll") for (int j = 0; j < STREAM_U; ++j)           \
+		{                                                              \
+			const int i = min(i0__ + j, (count)-1);                    \
+			LOADS                                                      \
+		}                                                              \
+		_Pragma("unroll") for (int j = 0; j < STREAM_U; ++j)           \
+		{                                                              \
+			const int i = i0__ + j;                                    \
+			if (i < (count)) { BODY }                                  \
+		}                                                              \
+	}
+
+template <int G>
+__global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kernel(const StreamView sv, const StreamLayout L, const StreamDims dm, const BatchIO io, const SolveParams prm, double *workspace, const int nslots, int *__restrict__ counter)
+{
+	extern __shared__ __align__(16) double smem[];
+	const unsigned FULL = 0xffffffffu;
+	const int lane = lane_id(), warp = threadIdx.x >> 5;
+	const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
+	if (slot >= nslots) return; // warps never wait for one another
+	double *tile = workspace + (size_t)slot * L.total * 32; // the warp's 32 interleaved slices
+	double *g = tile + lane;
+	const unsigned sb = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)(warp * L.scratch * 32 + lane) * 8u;
+	const int n = dm.n, m = dm.m, p = dm.p, np = dm.n + dm.p, N = dm.N;
+	const double thr = prm.reltol / sqrt(3.0);
+	SL(L.zero) = 0.0;
+	SL(L.one) = 1.0;
+	SL(L.mone) = -1.0;
+
+	int q = -1, iters = 0;
+	bool active = false, exhausted = false;
+	double sigma = 0.0, mu = 0.0, ap = 0.0, ad = 0.0;
+	Scalars sc;
+	sc.n_rx = sc.n_ry = sc.n_rz = sc.n_mu = sc.fval = 0.0;
+	double a8[STREAM_U], b8[STREAM_U], c8[STREAM_U], d8[STREAM_U], e8[STREAM_U];
+
+	for (;;) {
+		// ---- top of QP_SOLVE's loop (qpSWIFT.c:502-534): residuals, stop test ---------------------
+		int flag = -1;
+		if (active && iters >= prm.maxit) flag = 2; // QP_MAXIT (qpSWIFT.c:604-607)
+		const bool need_res = active && flag < 0;
+		if (__any_sync(FULL, need_res)) {
+			if (need_res) STREAM_FOR(m, a8[j] = SL(L.h + i); b8[j] = SL(L.s + i);, SL(L.hs + i) = a8[j] - b8[j];)
+			run_stream<G, true>(sv.words + sv.first[SSEG_RESID], sv.groups[SSEG_RESID], g, sb);
+			if (need_res) {
+				sc.n_rx = sqrt(stream_dot(g + (L.r << 5), g + (L.r << 5), n));
+				if (p) sc.n_ry = sqrt(stream_dot(g + ((L.r + n) << 5), g + ((L.r + n) << 5), p));
+				sc.n_rz = sqrt(stream_dot(g + ((L.r + np) << 5), g + ((L.r + np) << 5), m));
+				sc.n_mu = stream_dot(g + (L.s << 5), g + (L.z << 5), m) / m;
+				const double q1 = stream_dot(g + (L.px << 5), g + (L.x << 5), n), q2 = stream_dot(g + (L.c << 5), g + (L.x << 5), n);
+				sc.fval = -0.5 * q1 + q2;
+				if (sc.n_rx < thr && sc.n_rz < thr && (p == 0 || sc.n_ry < thr) && sc.n_mu < prm.abstol) flag = 0;
+			}
+		}
+		// ---- QPs that leave the loop: the warp writes them back, one finished lane at a time --------
+		unsigned done = __ballot_sync(FULL, active && flag >= 0);
+		__syncwarp();
+		while (done) {
+			const int src = __ffs(done) - 1;
+			done &= done - 1;
+			const size_t qi = (size_t)__shfl_sync(FULL, q, src);
+			const double *from = tile + src;
+			if (io.x) for (int e = lane; e < n; e += 32) io.x[qi * n + e] = from[(L.x + e) << 5];
+			if (io.y) for (int e = lane; e < p; e += 32) io.y[qi * p + e] = from[(L.y + e) << 5];
+			if (io.z) for (int e = lane; e < m; e += 32) io.z[qi * m + e] = from[(L.z + e) << 5];
+			if (io.s) for (int e = lane; e < m; e += 32) io.s[qi * m + e] = from[(L.s + e) << 5];
+		}
+		if (active && flag >= 0) {
+			if (io.flag) io.flag[q] = flag;
+			if (io.iters) io.iters[q] = iters;
+			if (io.fval) io.fval[q] = sc.fval;
+			if (io.stat) {
+				double *st = io.stat + (size_t)q * 8;
+				st[0] = sc.n_rx; st[1] = sc.n_ry; st[2] = sc.n_rz; st[3] = sc.n_mu;
+				st[4] = ap; st[5] = ad; st[6] = sigma; st[7] = mu;
+			}
+			active = false;
+		}
+		// ---- free lanes pull the next QPs of the batch -----------------------------------------------
+		int mode = SM_IDLE;
+		const unsigned want = __ballot_sync(FULL, !active && !exhausted);
+		if (want) {
+			int base = 0;
+			if (lane == 0) base = atomicAdd(counter, __popc(want));
+			base = __shfl_sync(FULL, base, 0);
+			bool fresh = false;
+			if (!active && !exhausted) {
+				q = base + __popc(want & ((1u << lane) - 1u));
+				if (q < io.count) fresh = true;
+				else { exhausted = true; q = -1; }
+			}
+			unsigned got = __ballot_sync(FULL, fresh);
+			while (got) { // the warp transposes one value row at a time into the owner's slice
+				const int dst = __ffs(got) - 1;
+				got &= got - 1;
+				const size_t qi = (size_t)__shfl_sync(FULL, q, dst);
+				double *to = tile + dst;
+				// "+ 0.0": the reference's Y[i] += value from Y[i] == 0 (ldl.c:284), see stream_program.h
+				for (int e = lane; e < dm.nnzP; e += 32) to[(L.V + e) << 5] = __ldg(io.Ppr + qi * dm.nnzP + e) + 0.0;
+				for (int e = lane; e < dm.nnzA; e += 32) to[(L.V + dm.nnzP + e) << 5] = __ldg(io.Apr + qi * dm.nnzA + e) + 0.0;
+				for (int e = lane; e < dm.nnzG; e += 32) to[(L.V + dm.nnzP + dm.nnzA + e) << 5] = __ldg(io.Gpr + qi * dm.nnzG + e) + 0.0;
+				for (int e = lane; e < n; e += 32) to[(L.c + e) << 5] = __ldg(io.c + qi * n + e);
+				for (int e = lane; e < m; e += 32) to[(L.h + e) << 5] = __ldg(io.h + qi * m + e);
+				for (int e = lane; e < p; e += 32) to[(L.b + e) << 5] = __ldg(io.b + qi * p + e);
+			}
+			__syncwarp();
+			if (fresh) { // kkt_initialize's system (Auxilary.c:1006-1030): rhs = [-c; b; h], (z,z) block = -I
+				STREAM_FOR(n, a8[j] = SL(L.c + i);, SL(L.rhs + i) = -a8[j];)
+				STREAM_FOR(p, a8[j] = SL(L.b + i);, SL(L.rhs + n + i) = a8[j];)
+				STREAM_FOR(m, a8[j] = SL(L.h + i);, SL(L.rhs + np + i) = a8[j]; SL(L.zd + i) = -1.0;)
+				iters = 0;
+				sigma = prm.sigma0;
+				mu = ap = ad = 0.0;
+				mode = SM_INIT;
+			}
+		}
+		// ---- an iteration of a running QP: lambda, mu, ds, W'W, right-hand side (qpSWIFT.c:537-552) ------
+		if (active) {
+			double acc = 0.0;
+			STREAM_FOR(m, a8[j] = SL(L.s + i); b8[j] = SL(L.z + i);,
+			           const double lam = sqrt(a8[j] * b8[j]); SL(L.lam + i) = lam; acc += lam * lam;
+			           SL(L.zd + i) = (-a8[j] / b8[j]) + 0.0;)
+			mu = acc / m;
+			double sm = 0.0;
+			if (sigma > prm.sigma_d) mode = SM_PRED;                         // predictor: ds = -lambda^2
+			else { sigma = prm.sigma_d; sm = sigma * mu; mode = SM_CENT; }   // centering step only (qpSWIFT.c:572-579)
+			const bool cent = mode == SM_CENT;
+			STREAM_FOR(m, a8[j] = SL(L.lam + i); b8[j] = SL(L.z + i); c8[j] = SL(L.r + np + i);,
+			           const double ds = cent ? -(a8[j] * a8[j]) + sm : -a8[j] * a8[j]; SL(L.ds + i) = ds;
+			           SL(L.rhs + np + i) = c8[j] - (ds / b8[j]);)
+			STREAM_FOR(np, a8[j] = SL(L.r + i);, SL(L.rhs + i) = a8[j];)
+		}
+		if (!__any_sync(FULL, mode != SM_IDLE)) break;
+
+		run_stream<G, false>(sv.words + sv.first[SSEG_FACTOR], sv.groups[SSEG_FACTOR], g, sb);
+		run_stream<G, false>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], g, sb);
+
+		// ---- kkt_initialize, second half (Auxilary.c:1044-1083) ------------------------------------------
+		if (__any_sync(FULL, mode == SM_INIT)) {
+			if (mode == SM_INIT) {
+				STREAM_FOR(n, a8[j] = SL(L.rhs + i);, SL(L.x + i) = a8[j];)
+				STREAM_FOR(p, a8[j] = SL(L.rhs + n + i);, SL(L.y + i) = a8[j];)
+				STREAM_FOR(m, a8[j] = SL(L.h + i);, SL(L.hs + i) = a8[j];)
+			}
+			run_stream<G, true>(sv.words + sv.first[SSEG_RESZ], sv.groups[SSEG_RESZ], g, sb); // hs <- h - G x
+			if (mode == SM_INIT) {
+				const double inf = __longlong_as_double(0x7ff0000000000000LL);
+				double lo = inf, hi = -inf;
+				STREAM_FOR(m, a8[j] = SL(L.hs + i);, if (a8[j] < lo) lo = a8[j]; if (a8[j] > hi) hi = a8[j];)
+				const double alpha_p = -lo, alpha_d = hi;
+				STREAM_FOR(m, a8[j] = SL(L.hs + i);,
+				           SL(L.s + i) = (alpha_p < 0) ? a8[j] : a8[j] + (1 + alpha_p);
+				           SL(L.z + i) = (alpha_d < 0) ? -a8[j] : -a8[j] + (1 + alpha_d);)
+				active = true;
+			}
+		}
+		// ---- delta_z, delta_s, step length, damping, update ------------------------------------------------
+		// (Auxilary.c:508-511, 359-393, 246-254; qpSWIFT.c:584-596)
+		auto step = [&](const bool take) {
+			double tp = 1e10, td = 1e10;
+			STREAM_FOR(m, a8[j] = SL(L.rhs + np + i); b8[j] = SL(L.ds + i); c8[j] = SL(L.s + i); d8[j] = SL(L.z + i);,
+			           const double dzi = a8[j]; const double dsi = (b8[j] - (c8[j] * dzi)) / d8[j];
+			           SL(L.dz + i) = dzi; SL(L.dsl + i) = dsi;
+			           if (dsi < 0 && (-c8[j] / dsi) < tp) tp = -(c8[j] / dsi);
+			           if (dzi < 0 && (-d8[j] / dzi) < td) td = -(d8[j] / dzi);)
+			ap = tp < 1e10 ? tp : 1.0;
+			ad = td < 1e10 ? td : 1.0;
+			if (!take) return;
+			ap = ((0.99 * ap) < (1.0)) ? (0.99 * ap) : (1.0);
+			ad = ((0.99 * ad) < (1.0)) ? (0.99 * ad) : (1.0);
+			STREAM_FOR(n, a8[j] = SL(L.x + i); b8[j] = SL(L.rhs + i);, SL(L.x + i) = a8[j] + b8[j] * ap;)
+			STREAM_FOR(p, a8[j] = SL(L.y + i); b8[j] = SL(L.rhs + n + i);, SL(L.y + i) = a8[j] + b8[j] * ad;)
+			STREAM_FOR(m, a8[j] = SL(L.s + i); b8[j] = SL(L.dsl + i); c8[j] = SL(L.z + i); d8[j] = SL(L.dz + i);,
+			           SL(L.s + i) = a8[j] + b8[j] * ap; SL(L.z + i) = c8[j] + d8[j] * ad;)
+			++iters;
+		};
+		if (mode == SM_CENT) step(true); // before the second solve overwrites this lane's solution
+		if (mode == SM_PRED) { // affine step, rho, sigma (Auxilary.c:879-892, qpSWIFT.c:566-567), corrector right-hand side
+			step(false);
+			double num = 0.0, den = 0.0;
+			STREAM_FOR(m, a8[j] = SL(L.s + i); b8[j] = SL(L.z + i); c8[j] = SL(L.dsl + i); d8[j] = SL(L.dz + i);,
+			           num += (a8[j] + (ap * c8[j])) * (b8[j] + (ad * d8[j])); den += a8[j] * b8[j];)
+			const double rho = num / den;
+			const double mr = (1 < rho) ? 1 : rho;
+			const double cube = mr * mr * mr;
+			sigma = (prm.sigma_d > cube) ? prm.sigma_d : cube;
+			const double sm = sigma * mu;
+			STREAM_FOR(m, a8[j] = SL(L.lam + i); b8[j] = SL(L.dsl + i); c8[j] = SL(L.dz + i); d8[j] = SL(L.z + i); e8[j] = SL(L.r + np + i);,
+			           const double ds = -(a8[j] * a8[j]) - (b8[j] * c8[j]) + sm; SL(L.ds + i) = ds;
+			           SL(L.rhs + np + i) = e8[j] - (ds / d8[j]);)
+			STREAM_FOR(np, a8[j] = SL(L.r + i);, SL(L.rhs + i) = a8[j];)
+		}
+		if (__any_sync(FULL, mode == SM_PRED)) {
+			run_stream<G, false>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], g, sb);
+			if (mode == SM_PRED) step(true);
+		}
+		(void)N;
+	}
+}
+
+#undef SL
+#undef STREAM_FOR
+
+#endif // __CUDACC__
+
+} // namespace qpb

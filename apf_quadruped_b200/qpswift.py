@@ -59,9 +59,9 @@ class QP(C.Structure):
 EXPORTS = [
     "QP_SETUP", "QP_SETUP_dense", "QP_SOLVE", "QP_CLEANUP", "QP_CLEANUP_dense",
     "QPB_PLAN_CREATE", "QPB_PLAN_DESTROY", "QPB_PLAN_ARRAY", "QPB_PLAN_INFO", "QPB_AMD_ORDER", "QPB_PLAN_PROGRAM",
-    "QPB_PLAN_LAYOUT",
+    "QPB_PLAN_LAYOUT", "QPB_PLAN_STREAM", "QPB_PLAN_STREAM_INFO",
     "QP_SETUP_BATCH", "QPB_BATCH_CREATE", "QP_SOLVE_BATCH", "QP_SOLVE_BATCH_DEVICE", "QP_CLEANUP_BATCH",
-    "QPB_BATCH_READ_STATS", "QPB_BATCH_SET_SIGMA_D", "QPB_BATCH_LAST_KERNEL_MS", "QPB_BATCH_LAST_LAUNCHES",
+    "QPB_BATCH_READ_STATS", "QPB_BATCH_SET_SIGMA_D", "QPB_BATCH_LAST_KERNEL_MS", "QPB_BATCH_LAST_LAUNCHES", "QPB_BATCH_LAST_KERNEL",
     "QPB_LDL_NUMERIC_BATCH", "QPB_LDL_SOLVE_BATCH", "QPB_LAST_ERROR", "QPB_DEVICE_COUNT",
 ]
 
@@ -95,6 +95,10 @@ def lib():
         lb.QPB_PLAN_PROGRAM.argtypes = [V, PL]
         lb.QPB_PLAN_LAYOUT.restype = L
         lb.QPB_PLAN_LAYOUT.argtypes = [V, C.POINTER(C.c_int), C.c_int]
+        lb.QPB_PLAN_STREAM.restype = C.POINTER(C.c_uint64)
+        lb.QPB_PLAN_STREAM.argtypes = [V, PL]
+        lb.QPB_PLAN_STREAM_INFO.restype = L
+        lb.QPB_PLAN_STREAM_INFO.argtypes = [V, C.POINTER(C.c_longlong), C.c_int]
         lb.QPB_AMD_ORDER.restype = L
         lb.QPB_AMD_ORDER.argtypes = [L, PL, PL, PL]
         lb.QP_SETUP_BATCH.restype = V
@@ -114,6 +118,8 @@ def lib():
         lb.QPB_BATCH_LAST_KERNEL_MS.argtypes = [V]
         lb.QPB_BATCH_LAST_LAUNCHES.restype = L
         lb.QPB_BATCH_LAST_LAUNCHES.argtypes = [V]
+        lb.QPB_BATCH_LAST_KERNEL.restype = C.c_int
+        lb.QPB_BATCH_LAST_KERNEL.argtypes = [V]
         lb.QPB_LDL_NUMERIC_BATCH.restype = L
         lb.QPB_LDL_NUMERIC_BATCH.argtypes = [V, L, V, V, V, V, V]
         lb.QPB_LDL_SOLVE_BATCH.restype = L
@@ -212,6 +218,34 @@ class Plan:
         lo = seg["first"] * 32
         return words[lo:lo + seg["waves"] * 32 * seg["width"]].reshape(seg["waves"], 32, seg["width"])
 
+    STREAM_LAYOUT = ["zero", "one", "mone", "V", "c", "h", "b", "zd", "Lx", "D", "rhs", "x", "y", "z", "s", "r", "lam", "ds", "dz",
+                     "dsl", "px", "hs", "total", "scratch"]
+    STREAM_SEGMENTS = ["factor", "solve", "resid", "resz"]
+    STREAM_STATS = ["first", "groups", "ops", "terms", "divs", "late", "hbm_loads", "hbm_stores", "nops", "slow_groups"]
+
+    def stream_info(self) -> dict:
+        """Layout, group size and per-segment statistics of the throughput kernel's micro-programs."""
+        buf = (C.c_longlong * 128)()
+        cnt = int(lib().QPB_PLAN_STREAM_INFO(self.handle, buf, 128))
+        nl = len(self.STREAM_LAYOUT)
+        assert cnt == nl + 2 + 10 * len(self.STREAM_SEGMENTS)
+        info = {"layout": {n: int(buf[i]) for i, n in enumerate(self.STREAM_LAYOUT)}, "ok": int(buf[nl]),
+                "group": int(buf[nl + 1]), "segments": {}}
+        for s, name in enumerate(self.STREAM_SEGMENTS):
+            base = nl + 2 + 10 * s
+            info["segments"][name] = {k: int(buf[base + i]) for i, k in enumerate(self.STREAM_STATS)}
+        return info
+
+    def stream_words(self, which: str | None = None) -> np.ndarray:
+        cnt = C.c_long()
+        ptr = lib().QPB_PLAN_STREAM(self.handle, C.byref(cnt))
+        words = np.ctypeslib.as_array(ptr, shape=(cnt.value,)).copy() if cnt.value else np.zeros(0, dtype=np.uint64)
+        if which is None:
+            return words
+        info = self.stream_info()
+        seg = info["segments"][which]
+        return words[seg["first"]:seg["first"] + seg["groups"] * info["group"]]
+
     def close(self):
         if self.handle:
             lib().QPB_PLAN_DESTROY(self.handle)
@@ -282,6 +316,10 @@ class BatchSolver:
     @property
     def last_kernel_ms(self) -> float:
         return float(lib().QPB_BATCH_LAST_KERNEL_MS(self.handle))
+
+    @property
+    def last_kernel(self) -> str:
+        return {0: "warp", 1: "stream"}.get(int(lib().QPB_BATCH_LAST_KERNEL(self.handle)), "?")
 
     @property
     def last_launches(self) -> int:

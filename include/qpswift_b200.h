@@ -80,6 +80,16 @@ qp_int QPB_PLAN_INFO(const QPBPlan *plan, int what);
 const unsigned long long *QPB_PLAN_PROGRAM(const QPBPlan *plan, qp_int *words);
 qp_int QPB_PLAN_LAYOUT(const QPBPlan *plan, int *out, int capacity);
 
+/* The micro-programs of the throughput kernel (csrc/stream_program.h): one thread per QP, working
+ * sets interleaved in HBM.  QPB_PLAN_STREAM: the 64-bit micro-op words of all segments.
+ * QPB_PLAN_STREAM_INFO: the slice layout {zero, one, mone, V, c, h, b, zd, Lx, D, rhs, x, y, z, s, r, lam, ds,
+ * dz, dsl, px, hs, total, scratch}, then {ok, micro-ops per group}, then for each segment (0 factor,
+ * 1 solve, 2 residuals, 3 h - G x) {first word, groups, micro-ops, multiply-subtracts, quotients, late
+ * loads, prefetched HBM loads, HBM stores, padding, slow groups}.  Returns the number of values available.
+ * Exposed so that the programs can be checked on the host (tests/test_stream_program.py). */
+const unsigned long long *QPB_PLAN_STREAM(const QPBPlan *plan, qp_int *words);
+qp_int QPB_PLAN_STREAM_INFO(const QPBPlan *plan, long long *out, int capacity);
+
 /* The ordering alone (test hook for amd_l_order, amd_order.c:21-199): returns the AMD status
  * (0 ok, 1 ok-but-jumbled, -2 invalid) and writes Perm[n]. */
 qp_int QPB_AMD_ORDER(qp_int n, const qp_int *Ap, const qp_int *Ai, qp_int *Perm);
@@ -123,6 +133,10 @@ qp_int QPB_BATCH_SET_SIGMA_D(QPBatch *batch, qp_real sigma_d);
 
 double QPB_BATCH_LAST_KERNEL_MS(const QPBatch *batch);
 qp_int QPB_BATCH_LAST_LAUNCHES(const QPBatch *batch);
+/* Which kernel the last solve used: 0 = latency kernel (one QP per warp, working set in shared
+ * memory; small batches), 1 = throughput kernel (one QP per thread, working sets interleaved in HBM;
+ * batches of at least QPB_STREAM_MIN [default 2048] QPs). */
+int QPB_BATCH_LAST_KERNEL(const QPBatch *batch);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel-level entry points (device pointers), used by the parity tests to check each

@@ -1,0 +1,78 @@
+"""GPU parity of the THROUGHPUT kernel (one QP per thread, csrc/stream.cuh) versus the CPU oracle.
+
+Same bar as tests/test_parity_gpu.py (which exercises the latency kernel with its small batches):
+identical exit flags and iteration counts, bit-identical x, y, z, s (the 1e-8 relative tolerance of
+BASELINE.json's north_star is the documented floor).  QPB_STREAM_MIN=1 sends every batch, however
+small, to the throughput kernel; the default threshold is covered by the last test.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from apf_quadruped_b200 import dogbot
+from test_parity_gpu import check_against_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def stream_only(monkeypatch):
+    monkeypatch.setenv("QPB_STREAM_MIN", "1")
+
+
+@pytest.mark.parametrize("kind,count", [("stance", 300), ("crawl", 97), ("trot", 300), ("mpc", 70)])
+def test_stream_batch_matches_oracle(qps, oracle, stream_only, kind, count):
+    """ragged counts: partial warps, lanes that run out of work at different times"""
+    batch = dogbot.generate(kind, count, start=40000)
+    solver = qps.BatchSolver(batch.pattern, count)
+    out = solver.solve(batch)
+    assert solver.last_kernel == "stream"
+    ref = oracle.solve_batch(batch)
+    check_against_oracle(out, ref)
+    fval, stat = solver.read_stats(count)
+    assert np.array_equal(fval, ref["fval"])
+    solver.close()
+
+
+def test_stream_controller_tolerances_and_maxit(qps, oracle, stream_only):
+    batch = dogbot.generate("trot", 130, start=5000)
+    solver = qps.BatchSolver(batch.pattern, 130)
+    out = solver.solve(batch, qps.default_settings(reltol=1e-2, abstol=1e-2))
+    check_against_oracle(out, oracle.solve_batch(batch, reltol=1e-2, abstol=1e-2))
+    out = solver.solve(batch, qps.default_settings(maxit=0))
+    assert np.all(out["flag"] == qps.QP_MAXIT) and np.all(out["iters"] == 0)
+    check_against_oracle(out, oracle.solve_batch(batch, maxit=0))
+    out = solver.solve(batch, qps.default_settings(maxit=3))
+    check_against_oracle(out, oracle.solve_batch(batch, maxit=3))
+    assert solver.last_kernel == "stream"
+    solver.close()
+
+
+def test_stream_user_permutation_and_sigma_d(qps, oracle, stream_only):
+    """sigma_d > 0 reaches the centering-only branch (qpSWIFT.c:572-579)"""
+    batch = dogbot.generate("crawl", 64, start=900)
+    pat = batch.pattern
+    perm = np.random.default_rng(5).permutation(pat.N)
+    solver = qps.BatchSolver(pat, 64, sigma_d=0.05, permut=perm)
+    out = solver.solve(batch)
+    assert solver.last_kernel == "stream"
+    check_against_oracle(out, oracle.solve_batch(batch, sigma_d=0.05, permut=perm))
+    solver.close()
+
+
+def test_stream_and_latency_kernels_agree_at_default_threshold(qps, oracle):
+    """4,096 trot QPs go to the throughput kernel by default; 512 of them to the latency kernel;
+    both are bit-identical with the oracle, so results do not depend on how a batch is cut."""
+    batch = dogbot.generate("trot", 4096, start=70000)
+    solver = qps.BatchSolver(batch.pattern, 4096)
+    out = solver.solve(batch)
+    assert solver.last_kernel == "stream"
+    ref, _ = oracle.run_batch(batch)
+    check_against_oracle(out, ref)
+    small = dogbot.generate("trot", 512, start=70000)
+    out2 = solver.solve(small)
+    assert solver.last_kernel == "warp"
+    for k in ("x", "y", "z", "s", "flag", "iters"):
+        assert np.array_equal(out2[k], out[k][:512])
+    solver.close()
