@@ -44,14 +44,17 @@ struct StreamDims
 #ifdef __CUDACC__
 
 // Interpreter.  g: the lane's slice (element e at g[e << 5]); sb: the lane's window of shared memory
-// (element e at sb + (e << 8)).  G micro-ops per group.  Software pipeline, per iteration:
-//   request the HBM operands of group i+1   (words fetched one iteration ago)
-//   fetch the words of group i+2
-//   execute group i                          (operands requested one iteration ago)
-// so two groups of operands (2G or 4G lines of 256 bytes per warp) are in flight while a group runs.
+// (element e at sb + (e << 8)); rb: the warp's instruction ring in shared memory.
+//
+// Instruction supply: the words are the same for every lane, so the warp reads them 3 groups (a
+// CHUNK) at a time with one coalesced load (lane l takes word l), parks the chunk in a two-chunk
+// ring in shared memory and every lane then reads each word as a broadcast.  Software pipeline, per
+// group i:   request the HBM operands of group i+2   (three operand buffers, rotated by unrolling)
+//            execute group i                          (operands requested two groups ago)
+// so two to three groups of operands (16-48 lines of 256 bytes per warp) are in flight while a group
+// runs, and chunk c+3 is on its way from L2 while chunk c executes.
 // A FAST group is executed without a single branch (flags become predicates and selects), a SLOW
-// group micro-op by micro-op; the words are the same in all lanes, a REDUX puts them into uniform
-// registers so that the dispatch costs no divergence handling.
+// group micro-op by micro-op (the words are the same in all lanes, so no branch ever diverges).
 // GG = false: factor / solve programs (second operand in the shared window); GG = true: residual
 // programs (second operand prefetched from HBM as well, results to HBM).
 // __noinline__: one copy serves all call sites (instruction cache).
@@ -64,101 +67,136 @@ __device__ __forceinline__ double ldg_now(const double *p)
 	asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
 	return v;
 }
-
-template <int G>
-__device__ __forceinline__ void fetch_words(uint2 (&dst)[G], const uint2 *__restrict__ prog)
+__device__ __forceinline__ uint2 lds_word(unsigned addr)
 {
-#pragma unroll
-	for (int u = 0; u < G; u += 2) {
-		const uint4 v = __ldg(reinterpret_cast<const uint4 *>(prog + u));
-		dst[u] = make_uint2(v.x, v.y);
-		dst[u + 1] = make_uint2(v.z, v.w);
-	}
+	uint2 v;
+	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+	return v;
 }
-
-template <int G, bool GG>
-__device__ __forceinline__ void request(const uint2 (&w)[G], double (&p1)[G], double (&p2)[GG ? G : 1], const double *g)
+__device__ __forceinline__ unsigned lds_u32(unsigned addr)
 {
-#pragma unroll
-	for (int u = 0; u < G; ++u) {
-		p1[u] = ldg_now(g + ((w[u].x & 0xffffu) << 5));
-		if (GG) p2[u] = ldg_now(g + ((w[u].x >> 16) << 5));
-	}
+	unsigned v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
 }
 
 #define HI(flag) ((unsigned)((flag) >> 32))
 
-template <int G, bool GG>
-__device__ __noinline__ void run_stream(const uint2 *__restrict__ prog, const int ngroups, double *g, const unsigned sb)
+// One micro-op of a SLOW group (quotients, pivots, copies, late operands).  A real call: slow groups
+// are a small share of the work and the interpreter has to stay small enough for the instruction cache.
+template <bool GG>
+__device__ __noinline__ double2 slow_op(const uint2 w, double P, const double S2, double t, double d, double *g, const unsigned sb)
 {
-	uint2 cur[G], nxt[G], far[G];
-	double p1[G], p2[GG ? G : 1], q1[G], q2[GG ? G : 1];
-	fetch_words<G>(cur, prog);
-	fetch_words<G>(nxt, prog + G);
-	request<G, GG>(cur, p1, p2, g);
-	prog += 2 * G;
-	double t = 0.0, d = 0.0;
-	for (int grp = 0; grp < ngroups; ++grp) {
-		request<G, GG>(nxt, q1, q2, g); // beyond the last group: the padding words point at a constant
-		fetch_words<G>(far, prog);
-		prog += G;
-		if (!__reduce_or_sync(0xffffffffu, cur[0].y & HI(SF_SLOW))) {
+	const unsigned lo = w.x, hi = w.y;
+	const unsigned op = (hi >> 16) & 15u;
+	if (hi & HI(SF_LATE1)) P = g[(lo & 0xffffu) << 5];
+	double S = 0.0;
+	if (GG) S = (hi & HI(SF_LATE2)) ? g[(lo >> 16) << 5] : S2;
+	else if (op == SOP_TERM || op == SOP_DIVACC || op == SOP_DIV || op == SOP_LOADS) S = lds64(sb + ((lo >> 16) << 8));
+	if (op == SOP_TERM) {
+		const double base = (hi & HI(SF_FIRSTZ)) ? 0.0 : t;
+		const double r = base - P * S;
+		t = (hi & HI(SF_INIT)) ? P : r;
+	} else if (op == SOP_DIVACC) {
+		t = S / P;
+		d = d - t * S;
+	} else if (op == SOP_DIV) t = S / P;
+	else if (op == SOP_INITD) d = P;
+	else if (op == SOP_ENDD) t = regularise(d);
+	else if (op == SOP_LOADS) t = S;
+	if (hi & HI(SF_ST_HBM)) g[(hi & 0xffffu) << 5] = t;
+	if (!GG && (hi & HI(SF_ST_SHARED))) sts64(sb + ((hi & 0xffffu) << 8), t);
+	return make_double2(t, d);
+}
+
+template <int G, bool GG>
+__device__ __forceinline__ void request(const unsigned words_at, double (&p1)[G], double (&p2)[GG ? G : 1], const double *g)
+{
+	unsigned lo[G];
 #pragma unroll
-			for (int u = 0; u < G; ++u) {
-				const unsigned lo = cur[u].x, hi = cur[u].y;
-				const double s = GG ? p2[u] : lds64(sb + ((lo >> 16) << 8));
-				const double base = (hi & HI(SF_FIRSTZ)) ? 0.0 : t;
-				const double r = base - p1[u] * s;
-				t = (hi & HI(SF_INIT)) ? p1[u] : r;
-				if (GG) {
-					if (hi & HI(SF_ST_HBM)) g[(hi & 0xffffu) << 5] = t;
-				} else {
-					if (hi & HI(SF_ST_SHARED)) sts64(sb + ((hi & 0xffffu) << 8), t);
-				}
-			}
-		} else {
-#pragma unroll 1
-			for (int u = 0; u < G; ++u) {
-				// (rolled: the words of slot u are selected below; slow groups are a small share of the work)
-				uint2 w = cur[0];
-				double P = p1[0], S2 = GG ? p2[0] : 0.0;
+	for (int u = 0; u < G; ++u) lo[u] = lds_u32(words_at + 8u * u);
 #pragma unroll
-				for (int v = 1; v < G; ++v)
-					if (v == u) { w = cur[v]; P = p1[v]; if (GG) S2 = p2[v]; }
-				const unsigned lo = __reduce_or_sync(0xffffffffu, w.x), hi = __reduce_or_sync(0xffffffffu, w.y);
-				const unsigned op = (hi >> 16) & 15u;
-				if (hi & HI(SF_LATE1)) P = g[(lo & 0xffffu) << 5];
-				double S = 0.0;
-				if (GG) S = (hi & HI(SF_LATE2)) ? g[(lo >> 16) << 5] : S2;
-				else if (op == SOP_TERM || op == SOP_DIVACC || op == SOP_DIV || op == SOP_LOADS) S = lds64(sb + ((lo >> 16) << 8));
-				if (op == SOP_TERM) {
-					const double base = (hi & HI(SF_FIRSTZ)) ? 0.0 : t;
-					const double r = base - P * S;
-					t = (hi & HI(SF_INIT)) ? P : r;
-				} else if (op == SOP_DIVACC) {
-					t = S / P;
-					d = d - t * S;
-				} else if (op == SOP_DIV) t = S / P;
-				else if (op == SOP_INITD) d = P;
-				else if (op == SOP_ENDD) t = regularise(d);
-				else if (op == SOP_LOADS) t = S;
-				if (hi & HI(SF_ST_HBM)) g[(hi & 0xffffu) << 5] = t;
-				if (!GG && (hi & HI(SF_ST_SHARED))) sts64(sb + ((hi & 0xffffu) << 8), t);
-			}
-		}
+	for (int u = 0; u < G; ++u) {
+		p1[u] = ldg_now(g + ((lo[u] & 0xffffu) << 5));
+		if (GG) p2[u] = ldg_now(g + ((lo[u] >> 16) << 5));
+	}
+}
+
+template <int G, bool GG>
+__device__ __forceinline__ void execute(const unsigned words_at, const double (&p1)[G], const double (&p2)[GG ? G : 1], double &t, double &d, double *g, const unsigned sb)
+{
+	uint2 w[G];
+#pragma unroll
+	for (int u = 0; u < G; ++u) w[u] = lds_word(words_at + 8u * u);
+	if (!(w[0].y & HI(SF_SLOW))) {
 #pragma unroll
 		for (int u = 0; u < G; ++u) {
-			cur[u] = nxt[u]; nxt[u] = far[u];
-			p1[u] = q1[u];
-			if (GG) p2[u] = q2[u];
+			const unsigned lo = w[u].x, hi = w[u].y;
+			const double s = GG ? p2[u] : lds64(sb + ((lo >> 16) << 8));
+			const double base = (hi & HI(SF_FIRSTZ)) ? 0.0 : t;
+			const double r = base - p1[u] * s;
+			t = (hi & HI(SF_INIT)) ? p1[u] : r;
+			if (GG) {
+				if (hi & HI(SF_ST_HBM)) g[(hi & 0xffffu) << 5] = t;
+			} else {
+				if (hi & HI(SF_ST_SHARED)) sts64(sb + ((hi & 0xffffu) << 8), t);
+			}
 		}
+		return;
+	}
+#pragma unroll
+	for (int u = 0; u < G; ++u) {
+		const double2 td = slow_op<GG>(w[u], p1[u], GG ? p2[u] : 0.0, t, d, g, sb);
+		t = td.x;
+		d = td.y;
+	}
+}
+
+// ngroups is a multiple of 3 (the compiler pads); the program is followed by 4 chunks of padding.
+template <int G, bool GG>
+__device__ __noinline__ void run_stream(const uint2 *__restrict__ prog, const int ngroups, double *g, const unsigned sb, const unsigned rb)
+{
+	const int lane = lane_id();
+	const unsigned CH = 3u * G * 8u; // bytes of a chunk
+	const bool loader = lane < 3 * G;
+	const uint2 *mine = prog + (loader ? lane : 0);
+	uint2 wreg = make_uint2(0u, 0u);
+	__syncwarp();
+	if (loader) {
+		const uint2 c0 = __ldg(mine), c1 = __ldg(mine + 3 * G);
+		wreg = __ldg(mine + 6 * G);
+		asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(rb + 8u * lane), "r"(c0.x), "r"(c0.y) : "memory");
+		asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(rb + CH + 8u * lane), "r"(c1.x), "r"(c1.y) : "memory");
+	}
+	mine += 9 * G;
+	__syncwarp();
+	double a1[G], a2[GG ? G : 1], b1[G], b2[GG ? G : 1], c1[G], c2[GG ? G : 1];
+	request<G, GG>(rb, a1, a2, g);
+	request<G, GG>(rb + G * 8u, b1, b2, g);
+	double t = 0.0, d = 0.0;
+	unsigned here = rb, there = rb + CH; // ring halves: the chunk being executed, the next one
+	for (int grp = 0; grp < ngroups; grp += 3) {
+		request<G, GG>(here + 2u * G * 8u, c1, c2, g);
+		execute<G, GG>(here, a1, a2, t, d, g, sb);
+		request<G, GG>(there, a1, a2, g);
+		execute<G, GG>(here + G * 8u, b1, b2, t, d, g, sb);
+		request<G, GG>(there + G * 8u, b1, b2, g);
+		execute<G, GG>(here + 2u * G * 8u, c1, c2, t, d, g, sb);
+		__syncwarp();
+		if (loader) {
+			asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(here + 8u * lane), "r"(wreg.x), "r"(wreg.y) : "memory");
+			wreg = __ldg(mine);
+		}
+		mine += 3 * G;
+		__syncwarp();
+		const unsigned swap = here; here = there; there = swap;
 	}
 }
 #undef HI
 
 // Sequential inner product sum_i a[i]*b[i] from 0.0 in ascending order (norm Auxilary.c:430-440,
 // innerproduct 451-462); the loads and products of eight terms are issued together.
-__device__ __forceinline__ double stream_dot(const double *a, const double *b, const int count)
+__device__ __noinline__ double stream_dot(const double *a, const double *b, const int count)
 {
 	double acc = 0.0;
 	for (int i0 = 0; i0 < count; i0 += 8) {
@@ -175,6 +213,11 @@ __device__ __forceinline__ double stream_dot(const double *a, const double *b, c
 	}
 	return acc;
 }
+
+// Out of line on purpose: an inlined FP64 division / square root is ~30 instructions, and the elementwise
+// steps below are unrolled eight-fold; the kernel has to stay friendly to the instruction cache.
+__device__ __noinline__ double div_rn(const double a, const double b) { return a / b; }
+__device__ __noinline__ double sqrt_rn(const double a) { return sqrt(a); }
 
 enum { SM_IDLE = 0, SM_INIT = 1, SM_PRED = 2, SM_CENT = 3 };
 static const int STREAM_MAX_WARPS = 8;
@@ -206,7 +249,9 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 	if (slot >= nslots) return; // warps never wait for one another
 	double *tile = workspace + (size_t)slot * L.total * 32; // the warp's 32 interleaved slices
 	double *g = tile + lane;
-	const unsigned sb = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)(warp * L.scratch * 32 + lane) * 8u;
+	const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+	const unsigned sb = sbase + (unsigned)(warp * L.scratch * 32 + lane) * 8u;
+	const unsigned rb = sbase + (unsigned)((blockDim.x >> 5) * L.scratch * 32) * 8u + (unsigned)warp * (6u * G * 8u); // instruction ring
 	const int n = dm.n, m = dm.m, p = dm.p, np = dm.n + dm.p, N = dm.N;
 	const double thr = prm.reltol / sqrt(3.0);
 	SL(L.zero) = 0.0;
@@ -227,7 +272,7 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 		const bool need_res = active && flag < 0;
 		if (__any_sync(FULL, need_res)) {
 			if (need_res) STREAM_FOR(m, a8[j] = SL(L.h + i); b8[j] = SL(L.s + i);, SL(L.hs + i) = a8[j] - b8[j];)
-			run_stream<G, true>(sv.words + sv.first[SSEG_RESID], sv.groups[SSEG_RESID], g, sb);
+			run_stream<G, true>(sv.words + sv.first[SSEG_RESID], sv.groups[SSEG_RESID], g, sb, rb);
 			if (need_res) {
 				sc.n_rx = sqrt(stream_dot(g + (L.r << 5), g + (L.r << 5), n));
 				if (p) sc.n_ry = sqrt(stream_dot(g + ((L.r + n) << 5), g + ((L.r + n) << 5), p));
@@ -304,8 +349,8 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 		if (active) {
 			double acc = 0.0;
 			STREAM_FOR(m, a8[j] = SL(L.s + i); b8[j] = SL(L.z + i);,
-			           const double lam = sqrt(a8[j] * b8[j]); SL(L.lam + i) = lam; acc += lam * lam;
-			           SL(L.zd + i) = (-a8[j] / b8[j]) + 0.0;)
+			           const double lam = sqrt_rn(a8[j] * b8[j]); SL(L.lam + i) = lam; acc += lam * lam;
+			           SL(L.zd + i) = div_rn(-a8[j], b8[j]) + 0.0;)
 			mu = acc / m;
 			double sm = 0.0;
 			if (sigma > prm.sigma_d) mode = SM_PRED;                         // predictor: ds = -lambda^2
@@ -313,13 +358,13 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 			const bool cent = mode == SM_CENT;
 			STREAM_FOR(m, a8[j] = SL(L.lam + i); b8[j] = SL(L.z + i); c8[j] = SL(L.r + np + i);,
 			           const double ds = cent ? -(a8[j] * a8[j]) + sm : -a8[j] * a8[j]; SL(L.ds + i) = ds;
-			           SL(L.rhs + np + i) = c8[j] - (ds / b8[j]);)
+			           SL(L.rhs + np + i) = c8[j] - div_rn(ds, b8[j]);)
 			STREAM_FOR(np, a8[j] = SL(L.r + i);, SL(L.rhs + i) = a8[j];)
 		}
 		if (!__any_sync(FULL, mode != SM_IDLE)) break;
 
-		run_stream<G, false>(sv.words + sv.first[SSEG_FACTOR], sv.groups[SSEG_FACTOR], g, sb);
-		run_stream<G, false>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], g, sb);
+		run_stream<G, false>(sv.words + sv.first[SSEG_FACTOR], sv.groups[SSEG_FACTOR], g, sb, rb);
+		run_stream<G, false>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], g, sb, rb);
 
 		// ---- kkt_initialize, second half (Auxilary.c:1044-1083) ------------------------------------------
 		if (__any_sync(FULL, mode == SM_INIT)) {
@@ -328,7 +373,7 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 				STREAM_FOR(p, a8[j] = SL(L.rhs + n + i);, SL(L.y + i) = a8[j];)
 				STREAM_FOR(m, a8[j] = SL(L.h + i);, SL(L.hs + i) = a8[j];)
 			}
-			run_stream<G, true>(sv.words + sv.first[SSEG_RESZ], sv.groups[SSEG_RESZ], g, sb); // hs <- h - G x
+			run_stream<G, true>(sv.words + sv.first[SSEG_RESZ], sv.groups[SSEG_RESZ], g, sb, rb); // hs <- h - G x
 			if (mode == SM_INIT) {
 				const double inf = __longlong_as_double(0x7ff0000000000000LL);
 				double lo = inf, hi = -inf;
@@ -345,10 +390,10 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 		auto step = [&](const bool take) {
 			double tp = 1e10, td = 1e10;
 			STREAM_FOR(m, a8[j] = SL(L.rhs + np + i); b8[j] = SL(L.ds + i); c8[j] = SL(L.s + i); d8[j] = SL(L.z + i);,
-			           const double dzi = a8[j]; const double dsi = (b8[j] - (c8[j] * dzi)) / d8[j];
+			           const double dzi = a8[j]; const double dsi = div_rn(b8[j] - (c8[j] * dzi), d8[j]);
 			           SL(L.dz + i) = dzi; SL(L.dsl + i) = dsi;
-			           if (dsi < 0 && (-c8[j] / dsi) < tp) tp = -(c8[j] / dsi);
-			           if (dzi < 0 && (-d8[j] / dzi) < td) td = -(d8[j] / dzi);)
+			           if (dsi < 0) { const double ratio = div_rn(c8[j], dsi); if (-ratio < tp) tp = -ratio; }
+			           if (dzi < 0) { const double ratio = div_rn(d8[j], dzi); if (-ratio < td) td = -ratio; })
 			ap = tp < 1e10 ? tp : 1.0;
 			ad = td < 1e10 ? td : 1.0;
 			if (!take) return;
@@ -373,11 +418,11 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 			const double sm = sigma * mu;
 			STREAM_FOR(m, a8[j] = SL(L.lam + i); b8[j] = SL(L.dsl + i); c8[j] = SL(L.dz + i); d8[j] = SL(L.z + i); e8[j] = SL(L.r + np + i);,
 			           const double ds = -(a8[j] * a8[j]) - (b8[j] * c8[j]) + sm; SL(L.ds + i) = ds;
-			           SL(L.rhs + np + i) = e8[j] - (ds / d8[j]);)
+			           SL(L.rhs + np + i) = e8[j] - div_rn(ds, d8[j]);)
 			STREAM_FOR(np, a8[j] = SL(L.r + i);, SL(L.rhs + i) = a8[j];)
 		}
 		if (__any_sync(FULL, mode == SM_PRED)) {
-			run_stream<G, false>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], g, sb);
+			run_stream<G, false>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], g, sb, rb);
 			if (mode == SM_PRED) step(true);
 		}
 		(void)N;

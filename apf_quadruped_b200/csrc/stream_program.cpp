@@ -49,11 +49,11 @@ struct Emitter
 		last_store.assign((size_t)prog.lay.total, -1);
 	}
 
-	// The kernel requests the HBM operands of group g+1 before it executes group g: an operand stored
-	// by the previous group or earlier in this one is not there yet.
+	// The kernel requests the HBM operands of group g+2 before it executes group g: an operand stored
+	// by the two previous groups or earlier in this one is not there yet.
 	bool is_late(int idx, int64_t at) const
 	{
-		const int64_t window_start = at - at % group - group;
+		const int64_t window_start = at - at % group - 2 * group;
 		return last_store[idx] >= 0 && last_store[idx] >= window_start;
 	}
 
@@ -120,6 +120,12 @@ struct Emitter
 	void end()
 	{
 		pad();
+		while ((pos() / group) % 3 != 0) { // the kernel runs three groups per turn of its pipeline
+			raw((uint64_t)prog.lay.zero | (gg ? (uint64_t)prog.lay.zero << 16 : 0), false);
+			++seg->nops;
+			++seg->ops;
+			pad();
+		}
 		seg->groups = (int32_t)(pos() / group);
 		for (int64_t g = 0; g < seg->groups; ++g)
 			if (prog.words[seg_start + (size_t)g * group] & SF_SLOW) ++seg->slow_groups;
@@ -282,8 +288,8 @@ bool build_stream_program(const Plan &pl, StreamProgram &prog, int group)
 	rz_chains(true);
 	E.end();
 
-	// the kernel fetches words two groups ahead
-	for (int i = 0; i < 2 * group; ++i) prog.words.push_back(((uint64_t)SOP_NOP << 48) | SF_SLOW | (uint64_t)L.zero);
+	// the kernel fetches words up to four chunks (of three groups) ahead
+	for (int i = 0; i < 12 * group; ++i) prog.words.push_back(((uint64_t)SOP_NOP << 48) | SF_SLOW | (uint64_t)L.zero);
 	L.scratch = even(std::max(maxpat, N));
 	if (E.overflow) { prog.error = "stream program: operand index out of range"; return false; }
 	prog.ok = true;

@@ -11,8 +11,8 @@
 // work vector Y of LDL_numeric and the work vector of the solves sit in a small per-lane window of
 // SHARED memory, everything else in the lane's slice of HBM -- and (3) which HBM operands can be
 // fetched ahead.  Micro-ops are executed in GROUPS; the kernel requests all HBM operands of group
-// g+1 before it executes the arithmetic of group g, so an operand that is stored by group g or by an
-// earlier micro-op of group g+1 is marked LATE (loaded at execution time instead).  A group is either
+// g+2 before it executes the arithmetic of group g, so an operand that is stored by groups g, g+1 or by
+// an earlier micro-op of group g+2 is marked LATE (loaded at execution time instead).  A group is either
 // FAST -- only multiply-subtracts and chain starts, executed branch-free -- or SLOW (quotients, pivots,
 // copies, late operands: interpreted micro-op by micro-op); the compiler pads with no-ops so that
 // the long runs of multiply-subtracts stay in fast groups.
@@ -87,7 +87,7 @@ struct StreamProgram
 {
 	StreamLayout lay;
 	int32_t group = 8; // micro-ops per group
-	std::vector<uint64_t> words; // segments, each padded to whole groups; one extra group of NOPs at the end
+	std::vector<uint64_t> words; // segments, each padded to a multiple of 3 groups; 12 groups of padding at the end
 	StreamSegment seg[SSEG_COUNT];
 	bool ok = false;
 	std::string error;

@@ -28,7 +28,7 @@ def decode(w):
 
 def run_stream(words, group, G, S, gg):
     """Execute micro-ops on the HBM slice G and the shared window S (float64 arrays), in place, with
-    the kernel's software pipeline: the HBM operands of group i+1 are read BEFORE group i executes.
+    the kernel's software pipeline: the HBM operands of group i+2 are read BEFORE group i executes.
     gg: residual program (second operand from HBM, results to HBM) instead of factor / solve."""
     assert len(words) % group == 0
     f = np.float64
@@ -38,12 +38,13 @@ def run_stream(words, group, G, S, gg):
     def request(ins):
         return [f(G[i["f1"]]) for i in ins], [f(G[i["f2"]]) if gg else None for i in ins]
 
+    assert len(groups) % 3 == 0, "the kernel's pipeline turns three groups at a time"
     with np.errstate(all="ignore"):
-        ahead = request(groups[0])
+        inflight = [request(g) for g in groups[:2]]
         for gi, ins in enumerate(groups):
-            p1, p2 = ahead
-            if gi + 1 < len(groups):
-                ahead = request(groups[gi + 1])
+            if gi + 2 < len(groups):
+                inflight.append(request(groups[gi + 2]))
+            p1, p2 = inflight.pop(0)
             slow = bool(ins[0]["w"] & SLOW)
             for u, i in enumerate(ins):
                 w, op = i["w"], i["op"]
