@@ -14,9 +14,12 @@ is the gather of solutions and exit flags the north_star names).
   e2e        the same metric through the reference-facing C ABI call QP_SOLVE_BATCH with HOST
              buffers (pinned): H2D of the value rows and D2H of x, y, z, s, flags, iterations inside
              the timed region.
-  roofline   dominant kernel (the fused interior-point kernel) against the measured HBM peak, using
-             SURVEY.md section 8d's algorithmic bytes per solve (see DESIGN.md "roofline"); plus the
-             stand-alone LDL factor / solve kernels under "kernels".
+  roofline   dominant kernel (the throughput kernel qp_solve_stream_kernel: one QP per thread, working
+             sets interleaved in HBM) against the measured HBM peak: "achieved" uses SURVEY.md section
+             8d's ALGORITHMIC bytes per solve (see DESIGN.md "roofline"), "traffic" is the kernel's real
+             DRAM traffic per launch from the committed ncu capture (profiles/ncu_traffic.json), and
+             "traffic_gbs" that traffic over the live launch time; plus the stand-alone LDL factor /
+             solve kernels under "kernels".
   cpu_baseline  the reference qpSWIFT (oracle/_ref, kind "reference"; else our port) on the box's
              host cores, one instance per thread, on a bounded sample of the same workload.
 
@@ -95,6 +98,16 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kind, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the solve kernel on this workload,
+    from the ncu --set full capture summarised under profiles/ (null when no capture matches)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    rec = json.load(open(path)).get(f"{kind}:{batch}")
+    return (float(rec["dram_bytes"]), rec.get("source")) if rec else (None, None)
+
+
 def algorithmic_bytes(plan, pat, iters):
     """per solve (it+1) B_factor + (2 it+1) B_solve + it B_vec."""
     N, lnz, nnzU = plan.info("N"), plan.info("lnz"), plan.info("nnzU")
@@ -166,9 +179,9 @@ def main():
             "z": torch.empty((B, pat.m), dtype=torch.float64, device=dev), "s": torch.empty((B, pat.m), dtype=torch.float64, device=dev),
             "flag": torch.empty(B, dtype=torch.int32, device=dev), "iters": torch.empty(B, dtype=torch.int32, device=dev)}
     gathered = None
+    width = pat.n + pat.p + 2 * pat.m + 2  # x | y | z | s | flag | iterations (apf_quadruped_b200/shard.py)
     if world > 1:
-        packed = torch.empty((B, pat.n + 2), dtype=torch.float64, device=dev)
-        gathered = torch.empty((world * B, pat.n + 2), dtype=torch.float64, device=dev)
+        gathered = torch.empty((world * B, width), dtype=torch.float64, device=dev)
 
     def ptr(t):
         return t.data_ptr() if t.numel() else None
@@ -179,9 +192,7 @@ def main():
                             ptr(dout["x"]), ptr(dout["y"]) if pat.p else None, ptr(dout["z"]), ptr(dout["s"]), ptr(dout["flag"]), ptr(dout["iters"]),
                             None, None, st)
         if world > 1:  # the only collective on the path: gather solutions + exit flags + iteration counts
-            packed[:, :pat.n] = dout["x"]
-            packed[:, pat.n] = dout["flag"].double()
-            packed[:, pat.n + 1] = dout["iters"].double()
+            packed = torch.cat([dout["x"], dout["y"][:, :pat.p], dout["z"], dout["s"], dout["flag"].double()[:, None], dout["iters"].double()[:, None]], dim=1)
             dist.all_gather_into_tensor(gathered, packed)
 
     def sync_all():
@@ -239,9 +250,15 @@ def main():
         peak, peak_src = peak_hbm()
         total_bytes, b_factor, b_solve, b_vec = algorithmic_bytes(solver.plan, pat, iters)
         achieved = total_bytes / (ms_step * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "qp_solve_fused_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_solve": total_bytes / B, "note": "fused kernel keeps L, D and the iterate in shared memory; 'achieved' uses SURVEY 8d's multi-kernel algorithmic bytes, DRAM traffic itself is only the value rows in and the solution out"}
+        traffic, traffic_src = ncu_traffic(args.kind, B)
+        stream = solver.last_kernel == "stream"
+        roof = {"bound": "hbm", "kernel": "qp_solve_stream_kernel" if stream else "qp_solve_cta_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_solve": total_bytes / B,
+                "traffic_gbs": traffic / (ms_step * 1e-3) / 1e9 if traffic else None, "traffic_source": traffic_src,
+                "note": ("one QP per thread, working sets interleaved in HBM: 'achieved' = SURVEY 8d algorithmic bytes (factor written once, read once per "
+                         "solve) / launch time; the up-looking factorisation re-reads L row by row, which is the gap between 'traffic' and the algorithmic bytes"
+                         if stream else "one QP per warp, working set in shared memory: DRAM traffic is only the value rows in and the solution out")}
         kernels = {}
         if not args.no_kernels:
             plan = solver.plan
