@@ -288,7 +288,7 @@ static int batch_alloc(QPBatch *B)
 	CUDA_TRY(cudaMalloc(&B->d_counter, 64 * sizeof(int)));
 	// ---- throughput kernel: one thread per QP, slices interleaved in an HBM workspace ---------------
 	if (B->sprog.ok) {
-		const size_t window = (size_t)B->sprog.lay.scratch * 32 * sizeof(double) + 6 * (size_t)B->sprog.group * 8; // shared memory per warp: work vector + instruction ring
+		const size_t window = (size_t)B->sprog.lay.scratch * 32 * sizeof(double); // shared memory per warp: the lanes' work vectors
 		long cap = getenv("QPB_STREAM_WARPS") ? atol(getenv("QPB_STREAM_WARPS")) : STREAM_MAX_WARPS;
 		if (cap > STREAM_MAX_WARPS) cap = STREAM_MAX_WARPS;
 		B->stream_warps = (int)std::min<size_t>((size_t)std::max(cap, 1L), B->smem_limit / window);
@@ -340,7 +340,7 @@ static int launch_stream(QPBatch *B, const BatchIO &io, const SolveParams &prm, 
 	long slots = std::min(B->stream_slots, ((long)io.count + 31) / 32);
 	const long warps = std::min<long>(B->stream_warps, std::max(1L, (slots + B->sm_count - 1) / B->sm_count));
 	const long grid = (slots + warps - 1) / warps;
-	const size_t smem = (size_t)warps * (sp.lay.scratch * 32 * sizeof(double) + 6 * (size_t)sp.group * 8);
+	const size_t smem = (size_t)warps * sp.lay.scratch * 32 * sizeof(double);
 	StreamDims dm;
 	dm.n = (int)B->plan.n; dm.m = (int)B->plan.m; dm.p = (int)B->plan.p; dm.N = (int)B->plan.N;
 	dm.nnzP = (int)B->plan.nnzP; dm.nnzA = (int)B->plan.nnzA; dm.nnzG = (int)B->plan.nnzG;

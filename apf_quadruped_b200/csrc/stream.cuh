@@ -44,15 +44,16 @@ struct StreamDims
 #ifdef __CUDACC__
 
 // Interpreter.  g: the lane's slice (element e at g[e << 5]); sb: the lane's window of shared memory
-// (element e at sb + (e << 8)); rb: the warp's instruction ring in shared memory.
+// (element e at sb + (e << 8)).
 //
-// Instruction supply: the words are the same for every lane, so the warp reads them 3 groups (a
-// CHUNK) at a time with one coalesced load (lane l takes word l), parks the chunk in a two-chunk
-// ring in shared memory and every lane then reads each word as a broadcast.  Software pipeline, per
-// group i:   request the HBM operands of group i+2   (three operand buffers, rotated by unrolling)
-//            execute group i                          (operands requested two groups ago)
-// so two to three groups of operands (16-48 lines of 256 bytes per warp) are in flight while a group
-// runs, and chunk c+3 is on its way from L2 while chunk c executes.
+// Instruction supply: the words are the same for every lane, so the warp reads them a CHUNK (DEPTH
+// groups of G micro-ops, at most 32) at a time with one coalesced load -- lane l takes word l, decodes it
+// once into byte offsets and flags -- and every lane then gets the fields of a micro-op with a shuffle
+// from its owner lane.  Software pipeline, per group i:
+//            request the HBM operands of group i+DEPTH-1   (DEPTH operand buffers, rotated by unrolling)
+//            execute group i                                (operands requested DEPTH-1 groups ago)
+// so DEPTH-1 groups of operands (24 to 48 lines of 256 bytes per warp) are in flight while a group
+// runs, and chunk c+2 is on its way from L2 while chunk c executes.
 // A FAST group is executed without a single branch (flags become predicates and selects), a SLOW
 // group micro-op by micro-op (the words are the same in all lanes, so no branch ever diverges).
 // GG = false: factor / solve programs (second operand in the shared window); GG = true: residual
@@ -61,42 +62,34 @@ struct StreamDims
 
 // A load the compiler may neither delay to its first use nor move into a branch: the requests of a
 // group have to be in flight together.
-__device__ __forceinline__ double ldg_now(const double *p)
+__device__ __forceinline__ double ldg_now(const char *p)
 {
 	double v;
 	asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
 	return v;
 }
-__device__ __forceinline__ uint2 lds_word(unsigned addr)
-{
-	uint2 v;
-	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-	return v;
-}
-__device__ __forceinline__ unsigned lds_u32(unsigned addr)
-{
-	unsigned v;
-	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-	return v;
-}
 
-#define HI(flag) ((unsigned)((flag) >> 32))
+// A decoded micro-op as its owner lane holds it: byte offsets of f1, f2, c and (op | flags << 4).
+#define LO(flag) ((unsigned)((flag) >> 48))
+__device__ __forceinline__ uint4 decode_word(const uint2 w)
+{
+	return make_uint4((w.x & 0xffffu) << 8, (w.x >> 16) << 8, (w.y & 0xffffu) << 8, w.y >> 16);
+}
 
 // One micro-op of a SLOW group (quotients, pivots, copies, late operands).  A real call: slow groups
 // are a small share of the work and the interpreter has to stay small enough for the instruction cache.
 template <bool GG>
-__device__ __noinline__ double2 slow_op(const uint2 w, double P, const double S2, double t, double d, double *g, const unsigned sb)
+__device__ __noinline__ double2 slow_op(const unsigned f1, const unsigned f2, const unsigned c, const unsigned fl, double P, const double S2, double t, double d, char *g, const unsigned sb)
 {
-	const unsigned lo = w.x, hi = w.y;
-	const unsigned op = (hi >> 16) & 15u;
-	if (hi & HI(SF_LATE1)) P = g[(lo & 0xffffu) << 5];
+	const unsigned op = fl & 15u;
+	if (fl & LO(SF_LATE1)) P = *reinterpret_cast<const double *>(g + f1);
 	double S = 0.0;
-	if (GG) S = (hi & HI(SF_LATE2)) ? g[(lo >> 16) << 5] : S2;
-	else if (op == SOP_TERM || op == SOP_DIVACC || op == SOP_DIV || op == SOP_LOADS) S = lds64(sb + ((lo >> 16) << 8));
+	if (GG) S = (fl & LO(SF_LATE2)) ? *reinterpret_cast<const double *>(g + f2) : S2;
+	else if (op == SOP_TERM || op == SOP_DIVACC || op == SOP_DIV || op == SOP_LOADS) S = lds64(sb + f2);
 	if (op == SOP_TERM) {
-		const double base = (hi & HI(SF_FIRSTZ)) ? 0.0 : t;
+		const double base = (fl & LO(SF_FIRSTZ)) ? 0.0 : t;
 		const double r = base - P * S;
-		t = (hi & HI(SF_INIT)) ? P : r;
+		t = (fl & LO(SF_INIT)) ? P : r;
 	} else if (op == SOP_DIVACC) {
 		t = S / P;
 		d = d - t * S;
@@ -104,95 +97,102 @@ __device__ __noinline__ double2 slow_op(const uint2 w, double P, const double S2
 	else if (op == SOP_INITD) d = P;
 	else if (op == SOP_ENDD) t = regularise(d);
 	else if (op == SOP_LOADS) t = S;
-	if (hi & HI(SF_ST_HBM)) g[(hi & 0xffffu) << 5] = t;
-	if (!GG && (hi & HI(SF_ST_SHARED))) sts64(sb + ((hi & 0xffffu) << 8), t);
+	if (fl & LO(SF_ST_HBM)) *reinterpret_cast<double *>(g + c) = t;
+	if (!GG && (fl & LO(SF_ST_SHARED))) sts64(sb + c, t);
 	return make_double2(t, d);
 }
 
+// slots [first, first + G) of `chunk`
 template <int G, bool GG>
-__device__ __forceinline__ void request(const unsigned words_at, double (&p1)[G], double (&p2)[GG ? G : 1], const double *g)
+__device__ __forceinline__ void request(const uint4 chunk, const int first, double (&p1)[G], double (&p2)[GG ? G : 1], const char *g)
 {
-	unsigned lo[G];
-#pragma unroll
-	for (int u = 0; u < G; ++u) lo[u] = lds_u32(words_at + 8u * u);
+	unsigned o1[G], o2[GG ? G : 1];
 #pragma unroll
 	for (int u = 0; u < G; ++u) {
-		p1[u] = ldg_now(g + ((lo[u] & 0xffffu) << 5));
-		if (GG) p2[u] = ldg_now(g + ((lo[u] >> 16) << 5));
+		o1[u] = __shfl_sync(0xffffffffu, chunk.x, first + u);
+		if (GG) o2[u] = __shfl_sync(0xffffffffu, chunk.y, first + u);
+	}
+#pragma unroll
+	for (int u = 0; u < G; ++u) {
+		p1[u] = ldg_now(g + o1[u]);
+		if (GG) p2[u] = ldg_now(g + o2[u]);
 	}
 }
 
 template <int G, bool GG>
-__device__ __forceinline__ void execute(const unsigned words_at, const double (&p1)[G], const double (&p2)[GG ? G : 1], double &t, double &d, double *g, const unsigned sb)
+__device__ __forceinline__ void execute(const uint4 chunk, const int first, const double (&p1)[G], const double (&p2)[GG ? G : 1], double &t, double &d, char *g, const unsigned sb)
 {
-	uint2 w[G];
+	unsigned f2[GG ? 1 : G], c[G], fl[G];
 #pragma unroll
-	for (int u = 0; u < G; ++u) w[u] = lds_word(words_at + 8u * u);
-	if (!(w[0].y & HI(SF_SLOW))) {
+	for (int u = 0; u < G; ++u) {
+		if (!GG) f2[u] = __shfl_sync(0xffffffffu, chunk.y, first + u);
+		c[u] = __shfl_sync(0xffffffffu, chunk.z, first + u);
+		fl[u] = __shfl_sync(0xffffffffu, chunk.w, first + u);
+	}
+	if (!(fl[0] & LO(SF_SLOW))) {
+		// No micro-op of a fast group reads what an earlier one of the same group stores (the compiler
+		// starts a new group instead): all second operands are read first, all results stored last, and
+		// in between only the accumulator links the micro-ops.
+		double s[G], out[G];
+#pragma unroll
+		for (int u = 0; u < G; ++u) s[u] = GG ? p2[u] : lds64(sb + f2[u]);
 #pragma unroll
 		for (int u = 0; u < G; ++u) {
-			const unsigned lo = w[u].x, hi = w[u].y;
-			const double s = GG ? p2[u] : lds64(sb + ((lo >> 16) << 8));
-			const double base = (hi & HI(SF_FIRSTZ)) ? 0.0 : t;
-			const double r = base - p1[u] * s;
-			t = (hi & HI(SF_INIT)) ? p1[u] : r;
+			const double base = (fl[u] & LO(SF_FIRSTZ)) ? 0.0 : t;
+			const double r = base - p1[u] * s[u];
+			t = (fl[u] & LO(SF_INIT)) ? p1[u] : r;
+			out[u] = t;
+		}
+#pragma unroll
+		for (int u = 0; u < G; ++u) {
 			if (GG) {
-				if (hi & HI(SF_ST_HBM)) g[(hi & 0xffffu) << 5] = t;
+				if (fl[u] & LO(SF_ST_HBM)) *reinterpret_cast<double *>(g + c[u]) = out[u];
 			} else {
-				if (hi & HI(SF_ST_SHARED)) sts64(sb + ((hi & 0xffffu) << 8), t);
+				if (fl[u] & LO(SF_ST_SHARED)) sts64(sb + c[u], out[u]);
 			}
 		}
 		return;
 	}
 #pragma unroll
 	for (int u = 0; u < G; ++u) {
-		const double2 td = slow_op<GG>(w[u], p1[u], GG ? p2[u] : 0.0, t, d, g, sb);
+		const unsigned f1 = __shfl_sync(0xffffffffu, chunk.x, first + u);
+		const unsigned g2 = GG ? __shfl_sync(0xffffffffu, chunk.y, first + u) : f2[GG ? 0 : u];
+		const double2 td = slow_op<GG>(f1, g2, c[u], fl[u], p1[u], GG ? p2[u] : 0.0, t, d, g, sb);
 		t = td.x;
 		d = td.y;
 	}
 }
 
-// ngroups is a multiple of 3 (the compiler pads); the program is followed by 4 chunks of padding.
-template <int G, bool GG>
-__device__ __noinline__ void run_stream(const uint2 *__restrict__ prog, const int ngroups, double *g, const unsigned sb, const unsigned rb)
+// ngroups is a multiple of DEPTH (the compiler pads); the program is followed by 4 chunks of padding.
+// DEPTH = groups per chunk = operand buffers.
+template <int G, bool GG, int DEPTH>
+__device__ __noinline__ void run_stream(const uint2 *__restrict__ prog, const int ngroups, double *slice, const unsigned sb)
 {
-	const int lane = lane_id();
-	const unsigned CH = 3u * G * 8u; // bytes of a chunk
-	const bool loader = lane < 3 * G;
-	const uint2 *mine = prog + (loader ? lane : 0);
-	uint2 wreg = make_uint2(0u, 0u);
-	__syncwarp();
-	if (loader) {
-		const uint2 c0 = __ldg(mine), c1 = __ldg(mine + 3 * G);
-		wreg = __ldg(mine + 6 * G);
-		asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(rb + 8u * lane), "r"(c0.x), "r"(c0.y) : "memory");
-		asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(rb + CH + 8u * lane), "r"(c1.x), "r"(c1.y) : "memory");
-	}
-	mine += 9 * G;
-	__syncwarp();
-	double a1[G], a2[GG ? G : 1], b1[G], b2[GG ? G : 1], c1[G], c2[GG ? G : 1];
-	request<G, GG>(rb, a1, a2, g);
-	request<G, GG>(rb + G * 8u, b1, b2, g);
+	constexpr int CH = DEPTH * G; // micro-ops per chunk, one per lane (lanes beyond CH idle along)
+	static_assert(CH <= 32, "a chunk is at most one micro-op per lane");
+	char *g = reinterpret_cast<char *>(slice);
+	const uint2 *mine = prog + (lane_id() < CH ? lane_id() : 0);
+	uint4 here = decode_word(__ldg(mine)), next = decode_word(__ldg(mine + CH));
+	uint2 far = __ldg(mine + 2 * CH);
+	mine += 3 * CH;
+	double p1[DEPTH][G], p2[DEPTH][GG ? G : 1];
+#pragma unroll
+	for (int k = 0; k + 1 < DEPTH; ++k) request<G, GG>(here, k * G, p1[k], p2[k], g);
 	double t = 0.0, d = 0.0;
-	unsigned here = rb, there = rb + CH; // ring halves: the chunk being executed, the next one
-	for (int grp = 0; grp < ngroups; grp += 3) {
-		request<G, GG>(here + 2u * G * 8u, c1, c2, g);
-		execute<G, GG>(here, a1, a2, t, d, g, sb);
-		request<G, GG>(there, a1, a2, g);
-		execute<G, GG>(here + G * 8u, b1, b2, t, d, g, sb);
-		request<G, GG>(there + G * 8u, b1, b2, g);
-		execute<G, GG>(here + 2u * G * 8u, c1, c2, t, d, g, sb);
-		__syncwarp();
-		if (loader) {
-			asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(here + 8u * lane), "r"(wreg.x), "r"(wreg.y) : "memory");
-			wreg = __ldg(mine);
+	for (int grp = 0; grp < ngroups; grp += DEPTH) {
+#pragma unroll
+		for (int k = 0; k < DEPTH; ++k) {
+			const int ahead = (k + DEPTH - 1) % DEPTH; // buffer (and group within its chunk) of group i + DEPTH - 1
+			request<G, GG>(k == 0 ? here : next, ahead * G, p1[ahead], p2[ahead], g);
+			execute<G, GG>(here, k * G, p1[k], p2[k], t, d, g, sb);
 		}
-		mine += 3 * G;
-		__syncwarp();
-		const unsigned swap = here; here = there; there = swap;
+		here = next;
+		next = decode_word(far);
+		far = __ldg(mine);
+		mine += CH;
 	}
 }
-#undef HI
+#undef LO
 
 // Sequential inner product sum_i a[i]*b[i] from 0.0 in ascending order (norm Auxilary.c:430-440,
 // innerproduct 451-462); the loads and products of eight terms are issued together.
@@ -249,9 +249,7 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 	if (slot >= nslots) return; // warps never wait for one another
 	double *tile = workspace + (size_t)slot * L.total * 32; // the warp's 32 interleaved slices
 	double *g = tile + lane;
-	const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
-	const unsigned sb = sbase + (unsigned)(warp * L.scratch * 32 + lane) * 8u;
-	const unsigned rb = sbase + (unsigned)((blockDim.x >> 5) * L.scratch * 32) * 8u + (unsigned)warp * (6u * G * 8u); // instruction ring
+	const unsigned sb = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)(warp * L.scratch * 32 + lane) * 8u;
 	const int n = dm.n, m = dm.m, p = dm.p, np = dm.n + dm.p, N = dm.N;
 	const double thr = prm.reltol / sqrt(3.0);
 	SL(L.zero) = 0.0;
@@ -272,7 +270,7 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 		const bool need_res = active && flag < 0;
 		if (__any_sync(FULL, need_res)) {
 			if (need_res) STREAM_FOR(m, a8[j] = SL(L.h + i); b8[j] = SL(L.s + i);, SL(L.hs + i) = a8[j] - b8[j];)
-			run_stream<G, true>(sv.words + sv.first[SSEG_RESID], sv.groups[SSEG_RESID], g, sb, rb);
+			run_stream<G, true, STREAM_GG_DEPTH(G)>(sv.words + sv.first[SSEG_RESID], sv.groups[SSEG_RESID], g, sb);
 			if (need_res) {
 				sc.n_rx = sqrt(stream_dot(g + (L.r << 5), g + (L.r << 5), n));
 				if (p) sc.n_ry = sqrt(stream_dot(g + ((L.r + n) << 5), g + ((L.r + n) << 5), p));
@@ -363,8 +361,8 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 		}
 		if (!__any_sync(FULL, mode != SM_IDLE)) break;
 
-		run_stream<G, false>(sv.words + sv.first[SSEG_FACTOR], sv.groups[SSEG_FACTOR], g, sb, rb);
-		run_stream<G, false>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], g, sb, rb);
+		run_stream<G, false, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_FACTOR], sv.groups[SSEG_FACTOR], g, sb);
+		run_stream<G, false, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], g, sb);
 
 		// ---- kkt_initialize, second half (Auxilary.c:1044-1083) ------------------------------------------
 		if (__any_sync(FULL, mode == SM_INIT)) {
@@ -373,7 +371,7 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 				STREAM_FOR(p, a8[j] = SL(L.rhs + n + i);, SL(L.y + i) = a8[j];)
 				STREAM_FOR(m, a8[j] = SL(L.h + i);, SL(L.hs + i) = a8[j];)
 			}
-			run_stream<G, true>(sv.words + sv.first[SSEG_RESZ], sv.groups[SSEG_RESZ], g, sb, rb); // hs <- h - G x
+			run_stream<G, true, STREAM_GG_DEPTH(G)>(sv.words + sv.first[SSEG_RESZ], sv.groups[SSEG_RESZ], g, sb); // hs <- h - G x
 			if (mode == SM_INIT) {
 				const double inf = __longlong_as_double(0x7ff0000000000000LL);
 				double lo = inf, hi = -inf;
@@ -422,7 +420,7 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 			STREAM_FOR(np, a8[j] = SL(L.r + i);, SL(L.rhs + i) = a8[j];)
 		}
 		if (__any_sync(FULL, mode == SM_PRED)) {
-			run_stream<G, false>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], g, sb, rb);
+			run_stream<G, false, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], g, sb);
 			if (mode == SM_PRED) step(true);
 		}
 		(void)N;

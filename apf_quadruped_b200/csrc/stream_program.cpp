@@ -29,9 +29,11 @@ struct Emitter
 	StreamSegment *seg = nullptr;
 	const int group;
 	bool gg = false;        // residual program: second operand from HBM, results to HBM
+	int depth = 4; // pipeline depth of the interpreter for this kind of program
 	size_t seg_start = 0;
 	bool cur_slow = false;  // class of the group being filled
 	std::vector<int64_t> last_store; // per slice double: position (within the segment) of the last HBM store, -1 none
+	std::vector<int64_t> last_window; // the same for the doubles of the shared window
 	bool overflow = false;
 
 	Emitter(StreamProgram &p) : prog(p), group(p.group) {}
@@ -45,15 +47,17 @@ struct Emitter
 		seg->first = (int32_t)prog.words.size();
 		seg_start = prog.words.size();
 		gg = residual;
+		depth = residual ? STREAM_GG_DEPTH(group) : STREAM_FS_DEPTH(group);
 		cur_slow = false;
 		last_store.assign((size_t)prog.lay.total, -1);
+		last_window.assign((size_t)prog.lay.total, -1);
 	}
 
-	// The kernel requests the HBM operands of group g+2 before it executes group g: an operand stored
-	// by the two previous groups or earlier in this one is not there yet.
+	// The kernel requests the HBM operands of group g+depth-1 before it executes group g: an operand
+	// stored by the depth-1 previous groups or earlier in this one is not there yet.
 	bool is_late(int idx, int64_t at) const
 	{
-		const int64_t window_start = at - at % group - 2 * group;
+		const int64_t window_start = at - at % group - (int64_t)(depth - 1) * group;
 		return last_store[idx] >= 0 && last_store[idx] >= window_start;
 	}
 
@@ -113,14 +117,27 @@ struct Emitter
 			if (code == SOP_TERM && !init) ++seg->terms;
 			if (code == SOP_DIV || code == SOP_DIVACC) ++seg->divs;
 			if (store == ST_HBM) { last_store[c] = at; ++seg->hbm_stores; }
+			if (store == ST_SHARED) last_window[c] = at;
 			return;
 		}
+	}
+
+	// A fast group reads all its window operands before it stores any result, so a chain must not
+	// read, in the group it starts in, what an earlier chain stored in that group.  Called where a
+	// chain starts (the accumulator is dead there, padding may clobber it).
+	void fresh_group_if_reads(const std::vector<int> &window_slots)
+	{
+		const int64_t at = pos();
+		const int filled = (int)(at % group);
+		if (filled == 0 || cur_slow) return; // a slow group executes micro-op by micro-op; a fast op leaves it anyway
+		for (int s : window_slots)
+			if (last_window[s] >= at - filled) { pad(); return; }
 	}
 
 	void end()
 	{
 		pad();
-		while ((pos() / group) % 3 != 0) { // the kernel runs three groups per turn of its pipeline
+		while ((pos() / group) % depth != 0) { // the kernel runs `depth` groups per turn of its pipeline
 			raw((uint64_t)prog.lay.zero | (gg ? (uint64_t)prog.lay.zero << 16 : 0), false);
 			++seg->nops;
 			++seg->ops;
@@ -141,6 +158,11 @@ struct Term
 // stores the result.  All of it fast-path words.
 void emit_chain(Emitter &E, int init, const std::vector<Term> &terms, int f2kind, int store, int c)
 {
+	if (f2kind == F2_SHARED) {
+		std::vector<int> reads;
+		for (const Term &t : terms) reads.push_back(t.b);
+		E.fresh_group_if_reads(reads);
+	}
 	bool started = false;
 	if (init >= 0 || terms.empty()) { // "+0.0 with nothing to subtract" starts from the constant
 		E.op(SOP_TERM, init, F2_NONE, 0, terms.empty() ? store : ST_NONE, c, false, true);
@@ -288,8 +310,8 @@ bool build_stream_program(const Plan &pl, StreamProgram &prog, int group)
 	rz_chains(true);
 	E.end();
 
-	// the kernel fetches words up to four chunks (of three groups) ahead
-	for (int i = 0; i < 12 * group; ++i) prog.words.push_back(((uint64_t)SOP_NOP << 48) | SF_SLOW | (uint64_t)L.zero);
+	// the kernel fetches words up to four chunks ahead
+	for (int i = 0; i < 4 * 32; ++i) prog.words.push_back(((uint64_t)SOP_NOP << 48) | SF_SLOW | (uint64_t)L.zero);
 	L.scratch = even(std::max(maxpat, N));
 	if (E.overflow) { prog.error = "stream program: operand index out of range"; return false; }
 	prog.ok = true;

@@ -11,8 +11,9 @@
 // work vector Y of LDL_numeric and the work vector of the solves sit in a small per-lane window of
 // SHARED memory, everything else in the lane's slice of HBM -- and (3) which HBM operands can be
 // fetched ahead.  Micro-ops are executed in GROUPS; the kernel requests all HBM operands of group
-// g+2 before it executes the arithmetic of group g, so an operand that is stored by groups g, g+1 or by
-// an earlier micro-op of group g+2 is marked LATE (loaded at execution time instead).  A group is either
+// g+DEPTH-1 before it executes the arithmetic of group g, so an operand that is stored by one of the
+// DEPTH-1 previous groups or by an earlier micro-op of its own group is marked LATE (loaded at
+// execution time instead).  A group is either
 // FAST -- only multiply-subtracts and chain starts, executed branch-free -- or SLOW (quotients, pivots,
 // copies, late operands: interpreted micro-op by micro-op); the compiler pads with no-ops so that
 // the long runs of multiply-subtracts stay in fast groups.
@@ -74,6 +75,12 @@ enum : uint64_t
 	SF_LATE2 = 1ull << 57,     // the same for the second HBM operand of a GG word
 	SF_SLOW = 1ull << 58       // set in EVERY word of a slow group
 };
+// Pipeline depth of the interpreter = groups per instruction chunk = operand buffers: the operands
+// of group g + DEPTH - 1 are requested before group g executes.  Factor / solve programs carry one
+// HBM operand per micro-op and keep 32 micro-ops in the pipeline (4 groups of 8), residual programs
+// carry two and keep 24.
+#define STREAM_FS_DEPTH(group) (32 / (group))
+#define STREAM_GG_DEPTH(group) (24 / (group))
 enum { SSEG_FACTOR = 0, SSEG_SOLVE = 1, SSEG_RESID = 2, SSEG_RESZ = 3, SSEG_COUNT = 4 };
 
 struct StreamSegment
@@ -87,7 +94,7 @@ struct StreamProgram
 {
 	StreamLayout lay;
 	int32_t group = 8; // micro-ops per group
-	std::vector<uint64_t> words; // segments, each padded to a multiple of 3 groups; 12 groups of padding at the end
+	std::vector<uint64_t> words; // segments, each padded to a multiple of its pipeline depth in groups; 16 groups of padding at the end
 	StreamSegment seg[SSEG_COUNT];
 	bool ok = false;
 	std::string error;

@@ -28,7 +28,7 @@ def decode(w):
 
 def run_stream(words, group, G, S, gg):
     """Execute micro-ops on the HBM slice G and the shared window S (float64 arrays), in place, with
-    the kernel's software pipeline: the HBM operands of group i+2 are read BEFORE group i executes.
+    the kernel's software pipeline: the HBM operands of group i+depth-1 are read BEFORE group i executes.
     gg: residual program (second operand from HBM, results to HBM) instead of factor / solve."""
     assert len(words) % group == 0
     f = np.float64
@@ -38,14 +38,18 @@ def run_stream(words, group, G, S, gg):
     def request(ins):
         return [f(G[i["f1"]]) for i in ins], [f(G[i["f2"]]) if gg else None for i in ins]
 
-    assert len(groups) % 3 == 0, "the kernel's pipeline turns three groups at a time"
+    depth = (24 if gg else 32) // group  # STREAM_GG_DEPTH / STREAM_FS_DEPTH
+    assert len(groups) % depth == 0, "the kernel's pipeline turns `depth` groups at a time"
     with np.errstate(all="ignore"):
-        inflight = [request(g) for g in groups[:2]]
+        inflight = [request(g) for g in groups[:depth - 1]]
         for gi, ins in enumerate(groups):
-            if gi + 2 < len(groups):
-                inflight.append(request(groups[gi + 2]))
+            if gi + depth - 1 < len(groups):
+                inflight.append(request(groups[gi + depth - 1]))
             p1, p2 = inflight.pop(0)
             slow = bool(ins[0]["w"] & SLOW)
+            if not slow:  # fast group: every second operand is read first, every result stored last
+                early = [f(S[i["f2"]]) if not gg else None for i in ins]
+            pending = []
             for u, i in enumerate(ins):
                 w, op = i["w"], i["op"]
                 assert bool(w & SLOW) == slow, "a group is fast or slow as a whole"
@@ -55,6 +59,8 @@ def run_stream(words, group, G, S, gg):
                 if gg:
                     Sv = f(G[i["f2"]]) if w & LATE2 else p2[u]
                     assert op in (TERM, NOP)
+                elif not slow:
+                    Sv = early[u]
                 else:
                     Sv = f(S[i["f2"]]) if op in (TERM, DIVACC, DIV, LOADS) else None
                 if op == TERM:
@@ -73,10 +79,18 @@ def run_stream(words, group, G, S, gg):
                     t = Sv
                 else:
                     assert op == NOP
+                if slow:
+                    if w & ST_HBM:
+                        G[i["c"]] = t
+                    if w & ST_SHARED:
+                        S[i["c"]] = t
+                else:
+                    pending.append((w, i["c"], t))
+            for w, c, v in pending:
                 if w & ST_HBM:
-                    G[i["c"]] = t
+                    G[c] = v
                 if w & ST_SHARED:
-                    S[i["c"]] = t
+                    S[c] = v
     return G
 
 
