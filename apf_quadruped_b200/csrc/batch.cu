@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -304,6 +305,10 @@ static int batch_alloc(QPBatch *B)
 		const long full = (long)B->sm_count * B->stream_warps;
 		B->stream_slots = std::min(full, (B->capacity + 31) / 32);
 		B->stream_min = getenv("QPB_STREAM_MIN") ? atol(getenv("QPB_STREAM_MIN")) : 2048;
+		// A pattern whose window leaves room for fewer than 4 warps per SM (e.g. the horizon-10 MPC QP:
+		// N = 600, one warp) is faster on the latency kernel; QPB_STREAM_MIN_WARPS overrides.
+		const long min_warps = getenv("QPB_STREAM_MIN_WARPS") ? atol(getenv("QPB_STREAM_MIN_WARPS")) : 4;
+		if (B->stream_warps < min_warps) B->stream_min = LONG_MAX;
 		if (B->capacity >= B->stream_min) CUDA_TRY(cudaMalloc(&B->d_workspace, (size_t)B->stream_slots * sp.lay.total * 32 * sizeof(double)));
 	}
 	CUDA_TRY(cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking));

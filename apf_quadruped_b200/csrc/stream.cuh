@@ -56,8 +56,8 @@ struct StreamDims
 // runs, and chunk c+2 is on its way from L2 while chunk c executes.
 // A FAST group is executed without a single branch (flags become predicates and selects), a SLOW
 // group micro-op by micro-op (the words are the same in all lanes, so no branch ever diverges).
-// GG = false: factor / solve programs (second operand in the shared window); GG = true: residual
-// programs (second operand prefetched from HBM as well, results to HBM).
+// GS = false: factor / solve programs (results to the shared window); GS = true: residual programs
+// (the window holds a copy of x | y | z, results to HBM).
 // __noinline__: one copy serves all call sites (instruction cache).
 
 // A load the compiler may neither delay to its first use nor move into a branch: the requests of a
@@ -71,6 +71,7 @@ __device__ __forceinline__ double ldg_now(const char *p)
 
 // A decoded micro-op as its owner lane holds it: byte offsets of f1, f2, c and (op | flags << 4).
 #define LO(flag) ((unsigned)((flag) >> 48))
+template <bool GS>
 __device__ __forceinline__ uint4 decode_word(const uint2 w)
 {
 	return make_uint4((w.x & 0xffffu) << 8, (w.x >> 16) << 8, (w.y & 0xffffu) << 8, w.y >> 16);
@@ -78,14 +79,13 @@ __device__ __forceinline__ uint4 decode_word(const uint2 w)
 
 // One micro-op of a SLOW group (quotients, pivots, copies, late operands).  A real call: slow groups
 // are a small share of the work and the interpreter has to stay small enough for the instruction cache.
-template <bool GG>
-__device__ __noinline__ double2 slow_op(const unsigned f1, const unsigned f2, const unsigned c, const unsigned fl, double P, const double S2, double t, double d, char *g, const unsigned sb)
+template <bool GS>
+__device__ __noinline__ double2 slow_op(const unsigned f1, const unsigned f2, const unsigned c, const unsigned fl, double P, double t, double d, char *g, const unsigned sb)
 {
 	const unsigned op = fl & 15u;
 	if (fl & LO(SF_LATE1)) P = *reinterpret_cast<const double *>(g + f1);
-	double S = 0.0;
-	if (GG) S = (fl & LO(SF_LATE2)) ? *reinterpret_cast<const double *>(g + f2) : S2;
-	else if (op == SOP_TERM || op == SOP_DIVACC || op == SOP_DIV || op == SOP_LOADS) S = lds64(sb + f2);
+	double S = 1.0;
+	if (!(fl & LO(SF_ONE)) && (op == SOP_TERM || op == SOP_DIVACC || op == SOP_DIV || op == SOP_LOADS)) S = lds64(sb + f2);
 	if (op == SOP_TERM) {
 		const double base = (fl & LO(SF_FIRSTZ)) ? 0.0 : t;
 		const double r = base - P * S;
@@ -98,34 +98,28 @@ __device__ __noinline__ double2 slow_op(const unsigned f1, const unsigned f2, co
 	else if (op == SOP_ENDD) t = regularise(d);
 	else if (op == SOP_LOADS) t = S;
 	if (fl & LO(SF_ST_HBM)) *reinterpret_cast<double *>(g + c) = t;
-	if (!GG && (fl & LO(SF_ST_SHARED))) sts64(sb + c, t);
+	if (!GS && (fl & LO(SF_ST_SHARED))) sts64(sb + c, t);
 	return make_double2(t, d);
 }
 
 // slots [first, first + G) of `chunk`
-template <int G, bool GG>
-__device__ __forceinline__ void request(const uint4 chunk, const int first, double (&p1)[G], double (&p2)[GG ? G : 1], const char *g)
+template <int G>
+__device__ __forceinline__ void request(const uint4 chunk, const int first, double (&p1)[G], const char *g)
 {
-	unsigned o1[G], o2[GG ? G : 1];
+	unsigned o1[G];
 #pragma unroll
-	for (int u = 0; u < G; ++u) {
-		o1[u] = __shfl_sync(0xffffffffu, chunk.x, first + u);
-		if (GG) o2[u] = __shfl_sync(0xffffffffu, chunk.y, first + u);
-	}
+	for (int u = 0; u < G; ++u) o1[u] = __shfl_sync(0xffffffffu, chunk.x, first + u);
 #pragma unroll
-	for (int u = 0; u < G; ++u) {
-		p1[u] = ldg_now(g + o1[u]);
-		if (GG) p2[u] = ldg_now(g + o2[u]);
-	}
+	for (int u = 0; u < G; ++u) p1[u] = ldg_now(g + o1[u]);
 }
 
-template <int G, bool GG>
-__device__ __forceinline__ void execute(const uint4 chunk, const int first, const double (&p1)[G], const double (&p2)[GG ? G : 1], double &t, double &d, char *g, const unsigned sb)
+template <int G, bool GS>
+__device__ __forceinline__ void execute(const uint4 chunk, const int first, const double (&p1)[G], double &t, double &d, char *g, const unsigned sb)
 {
-	unsigned f2[GG ? 1 : G], c[G], fl[G];
+	unsigned f2[G], c[G], fl[G];
 #pragma unroll
 	for (int u = 0; u < G; ++u) {
-		if (!GG) f2[u] = __shfl_sync(0xffffffffu, chunk.y, first + u);
+		f2[u] = __shfl_sync(0xffffffffu, chunk.y, first + u);
 		c[u] = __shfl_sync(0xffffffffu, chunk.z, first + u);
 		fl[u] = __shfl_sync(0xffffffffu, chunk.w, first + u);
 	}
@@ -135,17 +129,18 @@ __device__ __forceinline__ void execute(const uint4 chunk, const int first, cons
 		// in between only the accumulator links the micro-ops.
 		double s[G], out[G];
 #pragma unroll
-		for (int u = 0; u < G; ++u) s[u] = GG ? p2[u] : lds64(sb + f2[u]);
+		for (int u = 0; u < G; ++u) s[u] = lds64(sb + f2[u]);
 #pragma unroll
 		for (int u = 0; u < G; ++u) {
 			const double base = (fl[u] & LO(SF_FIRSTZ)) ? 0.0 : t;
-			const double r = base - p1[u] * s[u];
+			const double su = (GS && (fl[u] & LO(SF_ONE))) ? 1.0 : s[u];
+			const double r = base - p1[u] * su;
 			t = (fl[u] & LO(SF_INIT)) ? p1[u] : r;
 			out[u] = t;
 		}
 #pragma unroll
 		for (int u = 0; u < G; ++u) {
-			if (GG) {
+			if (GS) {
 				if (fl[u] & LO(SF_ST_HBM)) *reinterpret_cast<double *>(g + c[u]) = out[u];
 			} else {
 				if (fl[u] & LO(SF_ST_SHARED)) sts64(sb + c[u], out[u]);
@@ -156,8 +151,7 @@ __device__ __forceinline__ void execute(const uint4 chunk, const int first, cons
 #pragma unroll
 	for (int u = 0; u < G; ++u) {
 		const unsigned f1 = __shfl_sync(0xffffffffu, chunk.x, first + u);
-		const unsigned g2 = GG ? __shfl_sync(0xffffffffu, chunk.y, first + u) : f2[GG ? 0 : u];
-		const double2 td = slow_op<GG>(f1, g2, c[u], fl[u], p1[u], GG ? p2[u] : 0.0, t, d, g, sb);
+		const double2 td = slow_op<GS>(f1, f2[u], c[u], fl[u], p1[u], t, d, g, sb);
 		t = td.x;
 		d = td.y;
 	}
@@ -165,29 +159,29 @@ __device__ __forceinline__ void execute(const uint4 chunk, const int first, cons
 
 // ngroups is a multiple of DEPTH (the compiler pads); the program is followed by 4 chunks of padding.
 // DEPTH = groups per chunk = operand buffers.
-template <int G, bool GG, int DEPTH>
+template <int G, bool GS, int DEPTH>
 __device__ __noinline__ void run_stream(const uint2 *__restrict__ prog, const int ngroups, double *slice, const unsigned sb)
 {
 	constexpr int CH = DEPTH * G; // micro-ops per chunk, one per lane (lanes beyond CH idle along)
 	static_assert(CH <= 32, "a chunk is at most one micro-op per lane");
 	char *g = reinterpret_cast<char *>(slice);
 	const uint2 *mine = prog + (lane_id() < CH ? lane_id() : 0);
-	uint4 here = decode_word(__ldg(mine)), next = decode_word(__ldg(mine + CH));
+	uint4 here = decode_word<GS>(__ldg(mine)), next = decode_word<GS>(__ldg(mine + CH));
 	uint2 far = __ldg(mine + 2 * CH);
 	mine += 3 * CH;
-	double p1[DEPTH][G], p2[DEPTH][GG ? G : 1];
+	double p1[DEPTH][G];
 #pragma unroll
-	for (int k = 0; k + 1 < DEPTH; ++k) request<G, GG>(here, k * G, p1[k], p2[k], g);
+	for (int k = 0; k + 1 < DEPTH; ++k) request<G>(here, k * G, p1[k], g);
 	double t = 0.0, d = 0.0;
 	for (int grp = 0; grp < ngroups; grp += DEPTH) {
 #pragma unroll
 		for (int k = 0; k < DEPTH; ++k) {
 			const int ahead = (k + DEPTH - 1) % DEPTH; // buffer (and group within its chunk) of group i + DEPTH - 1
-			request<G, GG>(k == 0 ? here : next, ahead * G, p1[ahead], p2[ahead], g);
-			execute<G, GG>(here, k * G, p1[k], p2[k], t, d, g, sb);
+			request<G>(k == 0 ? here : next, ahead * G, p1[ahead], g);
+			execute<G, GS>(here, k * G, p1[k], t, d, g, sb);
 		}
 		here = next;
-		next = decode_word(far);
+		next = decode_word<GS>(far);
 		far = __ldg(mine);
 		mine += CH;
 	}
@@ -269,8 +263,12 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 		if (active && iters >= prm.maxit) flag = 2; // QP_MAXIT (qpSWIFT.c:604-607)
 		const bool need_res = active && flag < 0;
 		if (__any_sync(FULL, need_res)) {
-			if (need_res) STREAM_FOR(m, a8[j] = SL(L.h + i); b8[j] = SL(L.s + i);, SL(L.hs + i) = a8[j] - b8[j];)
-			run_stream<G, true, STREAM_GG_DEPTH(G)>(sv.words + sv.first[SSEG_RESID], sv.groups[SSEG_RESID], g, sb);
+			if (need_res) { // s - h (= -(h - s), exactly), and x | y | z into the window for the residual program
+				STREAM_FOR(m, a8[j] = SL(L.h + i); b8[j] = SL(L.s + i); c8[j] = SL(L.z + i);, SL(L.hs + i) = b8[j] - a8[j]; sts64(sb + ((unsigned)(np + i) << 8), c8[j]);)
+				STREAM_FOR(n, a8[j] = SL(L.x + i);, sts64(sb + ((unsigned)i << 8), a8[j]);)
+				STREAM_FOR(p, a8[j] = SL(L.y + i);, sts64(sb + ((unsigned)(n + i) << 8), a8[j]);)
+			}
+			run_stream<G, true, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_RESID], sv.groups[SSEG_RESID], g, sb);
 			if (need_res) {
 				sc.n_rx = sqrt(stream_dot(g + (L.r << 5), g + (L.r << 5), n));
 				if (p) sc.n_ry = sqrt(stream_dot(g + ((L.r + n) << 5), g + ((L.r + n) << 5), p));
@@ -330,7 +328,11 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 				for (int e = lane; e < dm.nnzG; e += 32) to[(L.V + dm.nnzP + dm.nnzA + e) << 5] = __ldg(io.Gpr + qi * dm.nnzG + e) + 0.0;
 				for (int e = lane; e < n; e += 32) to[(L.c + e) << 5] = __ldg(io.c + qi * n + e);
 				for (int e = lane; e < m; e += 32) to[(L.h + e) << 5] = __ldg(io.h + qi * m + e);
-				for (int e = lane; e < p; e += 32) to[(L.b + e) << 5] = __ldg(io.b + qi * p + e);
+				for (int e = lane; e < p; e += 32) {
+					const double be = __ldg(io.b + qi * p + e);
+					to[(L.b + e) << 5] = be;
+					to[(L.nb + e) << 5] = -be;
+				}
 			}
 			__syncwarp();
 			if (fresh) { // kkt_initialize's system (Auxilary.c:1006-1030): rhs = [-c; b; h], (z,z) block = -I
@@ -367,11 +369,11 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 		// ---- kkt_initialize, second half (Auxilary.c:1044-1083) ------------------------------------------
 		if (__any_sync(FULL, mode == SM_INIT)) {
 			if (mode == SM_INIT) {
-				STREAM_FOR(n, a8[j] = SL(L.rhs + i);, SL(L.x + i) = a8[j];)
+				STREAM_FOR(n, a8[j] = SL(L.rhs + i);, SL(L.x + i) = a8[j]; sts64(sb + ((unsigned)i << 8), a8[j]);) // x also into the window
 				STREAM_FOR(p, a8[j] = SL(L.rhs + n + i);, SL(L.y + i) = a8[j];)
-				STREAM_FOR(m, a8[j] = SL(L.h + i);, SL(L.hs + i) = a8[j];)
+				STREAM_FOR(m, a8[j] = SL(L.h + i);, SL(L.hs + i) = -a8[j];)
 			}
-			run_stream<G, true, STREAM_GG_DEPTH(G)>(sv.words + sv.first[SSEG_RESZ], sv.groups[SSEG_RESZ], g, sb); // hs <- h - G x
+			run_stream<G, true, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_RESZ], sv.groups[SSEG_RESZ], g, sb); // hs <- -(G x) - (-h) = h - G x
 			if (mode == SM_INIT) {
 				const double inf = __longlong_as_double(0x7ff0000000000000LL);
 				double lo = inf, hi = -inf;

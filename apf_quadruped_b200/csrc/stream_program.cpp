@@ -10,7 +10,7 @@
 //     terms of row r in ascending column order);  LDL_dsolve 520-532  w[j] /= D[j];
 //   LDL_ltsolve 539-557  w[j] -= Lx[q]*w[Li[q]], q ascending inside column j, j descending.
 //   computeresiduals Auxilary.c:745-786 (column scatter for P x, A x, G x; column gather for G'z, A'y);
-//     "+= c*(-1)", "+= b*1", "+= h - s" are exact as  t - c*1,  t - b*(-1),  t - (h-s)*(-1).
+//     "+= c*(-1)", "+= b*1", "+= h - s" are exact as  t - c,  t - (-b),  t - (s-h).
 
 #include "stream_program.h"
 
@@ -20,7 +20,7 @@
 namespace qpb {
 namespace {
 
-enum { F2_NONE = 0, F2_SHARED = 1, F2_HBM = 2 };
+enum { F2_NONE = 0, F2_SHARED = 1, F2_ONE = 2 };
 enum { ST_NONE = 0, ST_SHARED = 1, ST_HBM = 2 };
 
 struct Emitter
@@ -28,7 +28,7 @@ struct Emitter
 	StreamProgram &prog;
 	StreamSegment *seg = nullptr;
 	const int group;
-	bool gg = false;        // residual program: second operand from HBM, results to HBM
+	bool gs = false;        // residual program: window = copy of x | y | z, results to HBM
 	int depth = 4; // pipeline depth of the interpreter for this kind of program
 	size_t seg_start = 0;
 	bool cur_slow = false;  // class of the group being filled
@@ -46,8 +46,8 @@ struct Emitter
 		*seg = StreamSegment();
 		seg->first = (int32_t)prog.words.size();
 		seg_start = prog.words.size();
-		gg = residual;
-		depth = residual ? STREAM_GG_DEPTH(group) : STREAM_FS_DEPTH(group);
+		gs = residual;
+		depth = STREAM_FS_DEPTH(group);
 		cur_slow = false;
 		last_store.assign((size_t)prog.lay.total, -1);
 		last_window.assign((size_t)prog.lay.total, -1);
@@ -71,7 +71,7 @@ struct Emitter
 	{
 		while (pos() % group != 0) {
 			if (cur_slow) raw(((uint64_t)SOP_NOP << 48) | SF_SLOW | (uint64_t)prog.lay.zero, true);
-			else raw((uint64_t)prog.lay.zero | (gg ? (uint64_t)prog.lay.zero << 16 : 0), false); // TERM on +0.0: t is dead at every padding point
+			else raw((uint64_t)prog.lay.zero, false); // TERM on +0.0: t is dead at every padding point
 			++seg->nops;
 			++seg->ops;
 		}
@@ -88,13 +88,13 @@ struct Emitter
 	void op(int code, int f1, int f2kind, int f2, int store, int c, bool firstz = false, bool init = false)
 	{
 		if (f1 < 0) f1 = prog.lay.zero;
-		if (f2kind == F2_NONE) f2 = gg ? prog.lay.zero : 0;
+		if (f2kind != F2_SHARED) f2 = 0;
 		if (store == ST_NONE) c = 0;
 		if (f1 > 0xffff || f2 < 0 || f2 > 0xffff || c < 0 || c > 0xffff) overflow = true;
 		for (int attempt = 0;; ++attempt) {
 			const int64_t at = pos();
-			const bool late1 = is_late(f1, at), late2 = gg && is_late(f2, at);
-			const bool fast = code == SOP_TERM && !late1 && !late2 && store != (gg ? ST_SHARED : ST_HBM);
+			const bool late1 = is_late(f1, at);
+			const bool fast = code == SOP_TERM && !late1 && store != (gs ? ST_SHARED : ST_HBM);
 			const int filled = (int)(at % group);
 			if (filled != 0 && attempt == 0) {
 				if (fast && cur_slow) { pad(); continue; } // leave a slow group
@@ -108,8 +108,8 @@ struct Emitter
 			if (init) w |= SF_INIT;
 			if (store == ST_SHARED) w |= SF_ST_SHARED;
 			if (store == ST_HBM) w |= SF_ST_HBM;
+			if (f2kind == F2_ONE) w |= SF_ONE;
 			if (late1) { w |= SF_LATE1; ++seg->late; } else ++seg->hbm_loads;
-			if (gg) { if (late2) { w |= SF_LATE2; ++seg->late; } else ++seg->hbm_loads; }
 			const bool slow = filled == 0 ? !fast : cur_slow;
 			if (slow) w |= SF_SLOW;
 			raw(w, slow);
@@ -138,7 +138,7 @@ struct Emitter
 	{
 		pad();
 		while ((pos() / group) % depth != 0) { // the kernel runs `depth` groups per turn of its pipeline
-			raw((uint64_t)prog.lay.zero | (gg ? (uint64_t)prog.lay.zero << 16 : 0), false);
+			raw((uint64_t)prog.lay.zero, false);
 			++seg->nops;
 			++seg->ops;
 			pad();
@@ -158,7 +158,7 @@ struct Term
 // stores the result.  All of it fast-path words.
 void emit_chain(Emitter &E, int init, const std::vector<Term> &terms, int f2kind, int store, int c)
 {
-	if (f2kind == F2_SHARED) {
+	if (f2kind == F2_SHARED && !E.gs) {
 		std::vector<int> reads;
 		for (const Term &t : terms) reads.push_back(t.b);
 		E.fresh_group_if_reads(reads);
@@ -201,6 +201,7 @@ bool build_stream_program(const Plan &pl, StreamProgram &prog, int group)
 	L.lam = take(m); L.ds = take(m); L.dz = take(m); L.dsl = take(m);
 	L.px = take(n);
 	L.hs = take(m);
+	L.nb = take(p);
 	L.total = at;
 	if (L.total > 0xffff) { prog.error = "pattern too large: a QP's working set exceeds 65535 doubles"; return false; }
 
@@ -278,30 +279,33 @@ bool build_stream_program(const Plan &pl, StreamProgram &prog, int group)
 	E.end();
 
 	// ---- computeresiduals (+ the -(P x) of obj_value) ---------------------------------------------------
+	// The kernel copies x | y | z into the window first: every x[j], y[i], z[i] is used once per nonzero
+	// of its column / row, so only the matrix values travel from HBM.
+	const int wx = 0, wy = n, wz = n + p;
 	auto rz_chains = [&](bool in_place) {
 		for (int i = 0; i < m; ++i) {
 			std::vector<Term> t;
-			for (int q = grow_ptr[i]; q < grow_ptr[i + 1]; ++q) t.push_back({L.V + grow_val[q], L.x + grow_col[q]});
-			t.push_back({L.hs + i, L.mone}); // += (h - s)
-			emit_chain(E, -1, t, F2_HBM, ST_HBM, in_place ? L.hs + i : L.r + n + p + i);
+			for (int q = grow_ptr[i]; q < grow_ptr[i + 1]; ++q) t.push_back({L.V + grow_val[q], wx + grow_col[q]});
+			emit_chain(E, -1, t, F2_SHARED, ST_NONE, 0);
+			E.op(SOP_TERM, L.hs + i, F2_ONE, 0, ST_HBM, in_place ? L.hs + i : L.r + n + p + i); // += (h - s)
 		}
 	};
 	E.begin(SSEG_RESID, true);
 	for (int i = 0; i < n; ++i) {
 		// rx[i] = 0 - (P x)_i [kept as px[i] for obj_value, Auxilary.c:1136-1140] - (G'z)_i - (A'y)_i - c[i]
 		std::vector<Term> t;
-		for (int q = prow_ptr[i]; q < prow_ptr[i + 1]; ++q) t.push_back({L.V + prow_val[q], L.x + prow_col[q]});
-		emit_chain(E, -1, t, F2_HBM, ST_HBM, L.px + i);
-		for (int q = gcol_ptr[i]; q < gcol_ptr[i + 1]; ++q) E.op(SOP_TERM, L.V + offG + q, F2_HBM, L.z + gcol_row[q], ST_NONE, 0);
+		for (int q = prow_ptr[i]; q < prow_ptr[i + 1]; ++q) t.push_back({L.V + prow_val[q], wx + prow_col[q]});
+		emit_chain(E, -1, t, F2_SHARED, ST_HBM, L.px + i);
+		for (int q = gcol_ptr[i]; q < gcol_ptr[i + 1]; ++q) E.op(SOP_TERM, L.V + offG + q, F2_SHARED, wz + gcol_row[q], ST_NONE, 0);
 		if (p)
-			for (int q = acol_ptr[i]; q < acol_ptr[i + 1]; ++q) E.op(SOP_TERM, L.V + offA + q, F2_HBM, L.y + acol_row[q], ST_NONE, 0);
-		E.op(SOP_TERM, L.c + i, F2_HBM, L.one, ST_HBM, L.r + i);
+			for (int q = acol_ptr[i]; q < acol_ptr[i + 1]; ++q) E.op(SOP_TERM, L.V + offA + q, F2_SHARED, wy + acol_row[q], ST_NONE, 0);
+		E.op(SOP_TERM, L.c + i, F2_ONE, 0, ST_HBM, L.r + i);
 	}
 	for (int i = 0; i < p; ++i) {
 		std::vector<Term> t;
-		for (int q = arow_ptr[i]; q < arow_ptr[i + 1]; ++q) t.push_back({L.V + arow_val[q], L.x + arow_col[q]});
-		t.push_back({L.b + i, L.mone}); // += b
-		emit_chain(E, -1, t, F2_HBM, ST_HBM, L.r + n + i);
+		for (int q = arow_ptr[i]; q < arow_ptr[i + 1]; ++q) t.push_back({L.V + arow_val[q], wx + arow_col[q]});
+		emit_chain(E, -1, t, F2_SHARED, ST_NONE, 0);
+		E.op(SOP_TERM, L.nb + i, F2_ONE, 0, ST_HBM, L.r + n + i); // += b
 	}
 	rz_chains(false);
 	E.end();

@@ -40,7 +40,8 @@ struct StreamLayout
 	int32_t r;              // [N]  residuals rx|ry|rz
 	int32_t lam, ds, dz, dsl;
 	int32_t px;             // [n]  -(P x), kept for the objective value
-	int32_t hs;             // [m]  h - s going into the residual program; h - G x coming out of RESZ
+	int32_t hs;             // [m]  s - h going into the residual program (-h for the initial point); h - G x out of RESZ
+	int32_t nb;             // [p]  -b
 	int32_t total;          // doubles per slice
 	int32_t scratch;        // doubles of shared memory per lane
 };
@@ -48,12 +49,13 @@ struct StreamLayout
 // Micro-op word (64 bit):  f1 (16) | f2 << 16 | c << 32 | op << 48 (4 bits) | flags << 52
 //   f1  index of the PREFETCHED operand P in the lane's HBM slice (always fetched with its group; slots
 //       without one point at a constant)
-//   f2  second operand: in the factor / solve programs ("FS") an index S into the lane's window of shared
-//       memory, read at execution time; in the residual programs ("GG") a second prefetched HBM index
+//   f2  second operand: an index S into the lane's window of shared memory, read at execution time (the
+//       row-local Y / the work vector in the factor and solve programs, "FS"; a copy of x | y | z in the
+//       residual programs, "GS", whose results go to HBM)
 //   c   where the result goes (flags say whether it does, and into which space)
 // Every lane keeps two registers: t (chain accumulator) and d (the pivot being accumulated).
 // FAST groups hold only SOP_TERM words; their whole behaviour is in four flags:
-//       r = (FIRSTZ ? +0.0 : t) - P*S;   t = INIT ? P : r;   if ST_SHARED (FS) / ST_HBM (GG): [c] = t
+//       r = (FIRSTZ ? +0.0 : t) - P*(ONE ? 1.0 : S);   t = INIT ? P : r;   if ST_SHARED (FS) / ST_HBM (GS): [c] = t
 // (padding in a fast group is a TERM on the constant +0.0: it may clobber t, which is dead there).
 enum StreamOp
 {
@@ -72,15 +74,13 @@ enum : uint64_t
 	SF_ST_SHARED = 1ull << 54, // shared window[c] = t
 	SF_ST_HBM = 1ull << 55,    // HBM slice[c] = t
 	SF_LATE1 = 1ull << 56,     // P cannot be fetched ahead (stored too recently): fetch it at execution time
-	SF_LATE2 = 1ull << 57,     // the same for the second HBM operand of a GG word
+	SF_ONE = 1ull << 57,       // the second operand is the constant 1.0 (t = t - P: "+= c*(-1)", "+= b", "+= h - s")
 	SF_SLOW = 1ull << 58       // set in EVERY word of a slow group
 };
 // Pipeline depth of the interpreter = groups per instruction chunk = operand buffers: the operands
 // of group g + DEPTH - 1 are requested before group g executes.  Factor / solve programs carry one
-// HBM operand per micro-op and keep 32 micro-ops in the pipeline (4 groups of 8), residual programs
-// carry two and keep 24.
+// HBM operand per micro-op; 32 micro-ops are in the pipeline (4 groups of 8).
 #define STREAM_FS_DEPTH(group) (32 / (group))
-#define STREAM_GG_DEPTH(group) (24 / (group))
 enum { SSEG_FACTOR = 0, SSEG_SOLVE = 1, SSEG_RESID = 2, SSEG_RESZ = 3, SSEG_COUNT = 4 };
 
 struct StreamSegment

@@ -219,7 +219,7 @@ class Plan:
         return words[lo:lo + seg["waves"] * 32 * seg["width"]].reshape(seg["waves"], 32, seg["width"])
 
     STREAM_LAYOUT = ["zero", "one", "mone", "V", "c", "h", "b", "zd", "Lx", "D", "rhs", "x", "y", "z", "s", "r", "lam", "ds", "dz",
-                     "dsl", "px", "hs", "total", "scratch"]
+                     "dsl", "px", "hs", "nb", "total", "scratch"]
     STREAM_SEGMENTS = ["factor", "solve", "resid", "resz"]
     STREAM_STATS = ["first", "groups", "ops", "terms", "divs", "late", "hbm_loads", "hbm_stores", "nops", "slow_groups"]
 

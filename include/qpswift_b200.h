@@ -83,7 +83,7 @@ qp_int QPB_PLAN_LAYOUT(const QPBPlan *plan, int *out, int capacity);
 /* The micro-programs of the throughput kernel (csrc/stream_program.h): one thread per QP, working
  * sets interleaved in HBM.  QPB_PLAN_STREAM: the 64-bit micro-op words of all segments.
  * QPB_PLAN_STREAM_INFO: the slice layout {zero, one, mone, V, c, h, b, zd, Lx, D, rhs, x, y, z, s, r, lam, ds,
- * dz, dsl, px, hs, total, scratch}, then {ok, micro-ops per group}, then for each segment (0 factor,
+ * dz, dsl, px, hs, nb, total, scratch}, then {ok, micro-ops per group}, then for each segment (0 factor,
  * 1 solve, 2 residuals, 3 h - G x) {first word, groups, micro-ops, multiply-subtracts, quotients, late
  * loads, prefetched HBM loads, HBM stores, padding, slow groups}.  Returns the number of values available.
  * Exposed so that the programs can be checked on the host (tests/test_stream_program.py). */

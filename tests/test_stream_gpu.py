@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture()
 def stream_only(monkeypatch):
     monkeypatch.setenv("QPB_STREAM_MIN", "1")
+    monkeypatch.setenv("QPB_STREAM_MIN_WARPS", "1")  # also patterns that would default to the latency kernel (mpc)
 
 
 @pytest.mark.parametrize("kind,count", [("stance", 300), ("crawl", 97), ("trot", 300), ("mpc", 70)])

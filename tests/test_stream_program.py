@@ -12,7 +12,7 @@ import pytest
 from apf_quadruped_b200 import dogbot
 
 TERM, DIVACC, DIV, INITD, ENDD, LOADS, NOP = 0, 2, 3, 4, 5, 6, 8
-FIRSTZ, INIT, ST_SHARED, ST_HBM, LATE1, LATE2, SLOW = (1 << (52 + i) for i in range(7))
+FIRSTZ, INIT, ST_SHARED, ST_HBM, LATE1, ONE, SLOW = (1 << (52 + i) for i in range(7))
 
 
 def regularise(d):
@@ -26,39 +26,40 @@ def decode(w):
     return dict(f1=w & 0xffff, f2=(w >> 16) & 0xffff, c=(w >> 32) & 0xffff, op=(w >> 48) & 15, w=w)
 
 
-def run_stream(words, group, G, S, gg):
+def run_stream(words, group, G, S, gs):
     """Execute micro-ops on the HBM slice G and the shared window S (float64 arrays), in place, with
     the kernel's software pipeline: the HBM operands of group i+depth-1 are read BEFORE group i executes.
-    gg: residual program (second operand from HBM, results to HBM) instead of factor / solve."""
+    gs: residual program (the window holds x | y | z, results go to HBM) instead of factor / solve."""
     assert len(words) % group == 0
     f = np.float64
     t = d = f(np.nan)
     groups = [[decode(w) for w in words[g0:g0 + group]] for g0 in range(0, len(words), group)]
 
     def request(ins):
-        return [f(G[i["f1"]]) for i in ins], [f(G[i["f2"]]) if gg else None for i in ins]
+        return [f(G[i["f1"]]) for i in ins]
 
-    depth = (24 if gg else 32) // group  # STREAM_GG_DEPTH / STREAM_FS_DEPTH
+    depth = 32 // group  # STREAM_FS_DEPTH
     assert len(groups) % depth == 0, "the kernel's pipeline turns `depth` groups at a time"
     with np.errstate(all="ignore"):
         inflight = [request(g) for g in groups[:depth - 1]]
         for gi, ins in enumerate(groups):
             if gi + depth - 1 < len(groups):
                 inflight.append(request(groups[gi + depth - 1]))
-            p1, p2 = inflight.pop(0)
+            p1 = inflight.pop(0)
             slow = bool(ins[0]["w"] & SLOW)
             if not slow:  # fast group: every second operand is read first, every result stored last
-                early = [f(S[i["f2"]]) if not gg else None for i in ins]
+                early = [f(S[i["f2"]]) for i in ins]
             pending = []
             for u, i in enumerate(ins):
                 w, op = i["w"], i["op"]
                 assert bool(w & SLOW) == slow, "a group is fast or slow as a whole"
                 if not slow:  # the branch-free path knows four flags and nothing else
-                    assert op == TERM and not w & (LATE1 | LATE2) and not w & (ST_SHARED if gg else ST_HBM)
+                    assert op == TERM and not w & LATE1 and not w & (ST_SHARED if gs else ST_HBM)
                 P = f(G[i["f1"]]) if w & LATE1 else p1[u]
-                if gg:
-                    Sv = f(G[i["f2"]]) if w & LATE2 else p2[u]
-                    assert op in (TERM, NOP)
+                if gs:
+                    assert op in (TERM, NOP) and not w & ST_SHARED
+                if w & ONE:
+                    Sv = f(1.0)
                 elif not slow:
                     Sv = early[u]
                 else:
@@ -156,7 +157,9 @@ def test_stream_residual_programs(qps, kind):
     for name, v in (("x", x), ("y", y), ("z", z), ("s", s)):
         G[lay[name]:lay[name] + v.size] = v
     c, h, b = batch.c[0], batch.h[0], batch.b[0]
-    G[lay["hs"]:lay["hs"] + m] = h - s
+    G[lay["hs"]:lay["hs"] + m] = s - h
+    G[lay["nb"]:lay["nb"] + p] = -b
+    S[:n + p + m] = np.concatenate([x, y, z])  # the kernel copies the iterate into the window first
     run_stream(plan.stream_words("resid"), info["group"], G, S, True)
     # the reference's loops, literally
     Ppr, Apr, Gpr = batch.Ppr[0] + 0.0, batch.Apr[0] + 0.0, batch.Gpr[0] + 0.0
@@ -189,7 +192,7 @@ def test_stream_residual_programs(qps, kind):
     assert np.array_equal(r[:n], rx) and np.array_equal(r[n:n + p], ry) and np.array_equal(r[n + p:], rz)
     assert np.array_equal(G[lay["px"]:lay["px"] + n], px)
     # RESZ: hs <- -(G x) + hs in place (the initial point's r = h - G x with hs = h)
-    G[lay["hs"]:lay["hs"] + m] = h
+    G[lay["hs"]:lay["hs"] + m] = -h
     run_stream(plan.stream_words("resz"), info["group"], G, S, True)
     assert np.array_equal(G[lay["hs"]:lay["hs"] + m], rz0 + h)
 
