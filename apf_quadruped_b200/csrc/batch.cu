@@ -118,9 +118,13 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_CTA * 32, 1) qp_solve_cta_kernel
 			}
 		}
 		if (!active) { // next QP: load its value row, set up kkt_initialize's system
-			if (lane == 0) q = atomicAdd(counter, 1);
+			if (lane == 0) {
+				q = atomicAdd(counter, 1);
+				const int limit = io.count_ptr ? *io.count_ptr : io.count;
+				q = q < limit ? (io.index ? io.index[q] : q) : -1; // the QP behind the ticket
+			}
 			q = __shfl_sync(0xffffffffu, q, 0);
-			if (q < io.count) {
+			if (q >= 0) {
 				const size_t qi = (size_t)q;
 				warp_copy_in(w.V, io.Ppr + qi * pv.offA, pv.offA);
 				if (p) warp_copy_in(w.V + pv.offA, io.Apr + qi * (pv.offG - pv.offA), pv.offG - pv.offA);
@@ -235,6 +239,7 @@ struct QPBatch
 	int *d_plan = nullptr;
 	uint2 *d_prog = nullptr;
 	int *d_counter = nullptr;
+	int *d_spill = nullptr; // [capacity] QPs the throughput kernel handed over, d_counter[48] = how many
 	ProgramView pview;
 	int max_warps = 1;      // slices of shared memory that fit next to each other in one CTA
 	// throughput kernel (stream.cuh)
@@ -309,6 +314,7 @@ static int batch_alloc(QPBatch *B)
 		// N = 600, one warp) is faster on the latency kernel; QPB_STREAM_MIN_WARPS overrides.
 		const long min_warps = getenv("QPB_STREAM_MIN_WARPS") ? atol(getenv("QPB_STREAM_MIN_WARPS")) : 4;
 		if (B->stream_warps < min_warps) B->stream_min = LONG_MAX;
+		if (B->capacity >= B->stream_min) CUDA_TRY(cudaMalloc(&B->d_spill, (size_t)B->capacity * sizeof(int)));
 		if (B->capacity >= B->stream_min) CUDA_TRY(cudaMalloc(&B->d_workspace, (size_t)B->stream_slots * sp.lay.total * 32 * sizeof(double)));
 	}
 	CUDA_TRY(cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking));
@@ -338,8 +344,27 @@ static int batch_alloc_staging(QPBatch *B)
 	return 0;
 }
 
-// Large batches: one thread per QP (stream.cuh).  One CTA per SM, stream_warps warps each.
-static int launch_stream(QPBatch *B, const BatchIO &io, const SolveParams &prm, cudaStream_t st)
+static int launch_latency(QPBatch *B, const BatchIO &io, const SolveParams &prm, long count, int *counter, cudaStream_t st)
+{
+	// one persistent CTA per SM; small batches spread over the SMs with fewer warps per CTA
+	long warps = (count + B->sm_count - 1) / B->sm_count;
+	if (warps > B->max_warps) warps = B->max_warps;
+	if (warps < 1) warps = 1;
+	long grid = (count + warps - 1) / warps;
+	if (grid > B->sm_count) grid = B->sm_count;
+	const size_t smem = (size_t)warps * B->program.lay.total * sizeof(double);
+	qp_solve_cta_kernel<<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->d_plan, B->pview, B->program.lay, io, prm, counter);
+	CUDA_TRY(cudaGetLastError());
+	return 0;
+}
+
+// Large batches: one thread per QP (stream.cuh).  One CTA per SM, stream_warps warps each.  A QP that
+// needs far more iterations than its neighbours (the ~1 % of trot QPs that run into maxit = 100) would keep
+// its warp -- and the launch -- alive long after the batch is done, at one thread's pace; the throughput
+// kernel therefore hands every QP that has not converged after QPB_STREAM_SPILL iterations (default 32)
+// over to the latency kernel, which solves those few from scratch with a warp each.  Results do not
+// depend on which kernel produced them (both are bit-identical with the reference).
+static int launch_stream(QPBatch *B, BatchIO io, SolveParams prm, cudaStream_t st)
 {
 	const StreamProgram &sp = B->sprog;
 	long slots = std::min(B->stream_slots, ((long)io.count + 31) / 32);
@@ -349,16 +374,34 @@ static int launch_stream(QPBatch *B, const BatchIO &io, const SolveParams &prm, 
 	StreamDims dm;
 	dm.n = (int)B->plan.n; dm.m = (int)B->plan.m; dm.p = (int)B->plan.p; dm.N = (int)B->plan.N;
 	dm.nnzP = (int)B->plan.nnzP; dm.nnzA = (int)B->plan.nnzA; dm.nnzG = (int)B->plan.nnzG;
+	const long spill = getenv("QPB_STREAM_SPILL") ? atol(getenv("QPB_STREAM_SPILL")) : 32;
+	prm.spill_after = spill > 0 && spill < prm.maxit ? (int)spill : 0;
+	int *spill_count = B->d_counter + 48, *second_counter = B->d_counter + 56;
+	if (prm.spill_after) {
+		CUDA_TRY(cudaMemsetAsync(spill_count, 0, 16 * sizeof(int), st));
+		io.spill = B->d_spill;
+		io.spill_count = spill_count;
+	}
 	if (sp.group == 4) qp_solve_stream_kernel<4><<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->sview, sp.lay, dm, io, prm, B->d_workspace, (int)slots, B->d_counter);
 	else if (sp.group == 8) qp_solve_stream_kernel<8><<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->sview, sp.lay, dm, io, prm, B->d_workspace, (int)slots, B->d_counter);
 	else return fail(QPB_E_ARG, "stream program: unsupported group size", cudaSuccess);
 	CUDA_TRY(cudaGetLastError());
 	B->last_launches = 1;
 	B->last_kernel = 1;
+	if (prm.spill_after) { // the stragglers: how many is only known on the device, so the launch is sized for "a few per SM"
+		io.index = B->d_spill;
+		io.count_ptr = spill_count;
+		io.spill = nullptr;
+		io.spill_count = nullptr;
+		prm.spill_after = 0;
+		const int rc = launch_latency(B, io, prm, (long)B->sm_count * B->max_warps, second_counter, st);
+		if (rc) return rc;
+		B->last_launches = 2;
+	}
 	return 0;
 }
 
-static int launch_fused(QPBatch *B, const BatchIO &io, const settings *opts, cudaStream_t st)
+static int launch_fused(QPBatch *B, BatchIO io, const settings *opts, cudaStream_t st)
 {
 	SolveParams prm;
 	prm.maxit = (int)opts->maxit;
@@ -366,20 +409,16 @@ static int launch_fused(QPBatch *B, const BatchIO &io, const settings *opts, cud
 	prm.abstol = opts->abstol;
 	prm.sigma0 = opts->sigma;
 	prm.sigma_d = B->sigma_d;
+	prm.spill_after = 0;
+	io.index = nullptr;
+	io.count_ptr = nullptr;
+	io.spill = nullptr;
+	io.spill_count = nullptr;
 	CUDA_TRY(cudaMemsetAsync(B->d_counter, 0, sizeof(int), st));
 	if (B->d_workspace && io.count >= B->stream_min) return launch_stream(B, io, prm, st);
 	B->last_kernel = 0;
-	// one persistent CTA per SM; small batches spread over the SMs with fewer warps per CTA
-	long warps = (io.count + B->sm_count - 1) / B->sm_count;
-	if (warps > B->max_warps) warps = B->max_warps;
-	if (warps < 1) warps = 1;
-	long grid = (io.count + warps - 1) / warps;
-	if (grid > B->sm_count) grid = B->sm_count;
-	const size_t smem = (size_t)warps * B->program.lay.total * sizeof(double);
-	qp_solve_cta_kernel<<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->d_plan, B->pview, B->program.lay, io, prm, B->d_counter);
-	CUDA_TRY(cudaGetLastError());
 	B->last_launches = 1;
-	return 0;
+	return launch_latency(B, io, prm, io.count, B->d_counter, st);
 }
 
 extern "C" {
@@ -426,6 +465,7 @@ void QP_CLEANUP_BATCH(QPBatch *B)
 	cudaFree(B->d_prog);
 	cudaFree(B->d_stream);
 	cudaFree(B->d_workspace);
+	cudaFree(B->d_spill);
 	cudaFree(B->d_counter);
 	for (int i = 0; i < 6; ++i) cudaFree(B->d_in[i]);
 	cudaFree(B->d_x); cudaFree(B->d_y); cudaFree(B->d_z); cudaFree(B->d_s);

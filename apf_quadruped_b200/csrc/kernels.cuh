@@ -33,6 +33,7 @@ struct SolveParams
 {
 	int maxit;
 	double reltol, abstol, sigma0, sigma_d;
+	int spill_after; // throughput kernel: hand a QP that has not converged after this many iterations to the latency kernel (0: never)
 };
 
 struct BatchIO
@@ -42,6 +43,10 @@ struct BatchIO
 	int *flag, *iters;
 	double *fval, *stat;                       // [count], [count][8] (may be null)
 	int count;
+	// second pass over the stragglers of the throughput kernel: solve QP index[i], i < *count_ptr
+	const int *index;     // null: QP i is QP i
+	const int *count_ptr; // null: count
+	int *spill, *spill_count; // throughput kernel: where it lists the QPs it hands over (null: it never does)
 };
 
 #ifdef __CUDACC__

@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 		// ---- top of QP_SOLVE's loop (qpSWIFT.c:502-534): residuals, stop test ---------------------
 		int flag = -1;
 		if (active && iters >= prm.maxit) flag = 2; // QP_MAXIT (qpSWIFT.c:604-607)
+		else if (active && prm.spill_after && iters >= prm.spill_after) flag = 4; // a straggler: the latency kernel takes it (batch.cu)
 		const bool need_res = active && flag < 0;
 		if (__any_sync(FULL, need_res)) {
 			if (need_res) { // s - h (= -(h - s), exactly), and x | y | z into the window for the residual program
@@ -280,6 +281,11 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 			}
 		}
 		// ---- QPs that leave the loop: the warp writes them back, one finished lane at a time --------
+		if (active && flag == 4) {
+			io.spill[atomicAdd(io.spill_count, 1)] = q;
+			active = false;
+			flag = -1;
+		}
 		unsigned done = __ballot_sync(FULL, active && flag >= 0);
 		__syncwarp();
 		while (done) {

@@ -78,7 +78,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.5)
 
     def summary(self):
         self.stop_flag.set()
@@ -164,8 +164,11 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION/INFO; stdout carries exactly one JSON line
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
+        # NCCL prints its version banner on stdout at any NCCL_DEBUG level; stdout carries exactly one JSON line
+        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("BENCH_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch
@@ -181,7 +184,10 @@ def main():
             "z": torch.empty((B, pat.m), dtype=torch.float64, device=dev), "s": torch.empty((B, pat.m), dtype=torch.float64, device=dev),
             "flag": torch.empty(B, dtype=torch.int32, device=dev), "iters": torch.empty(B, dtype=torch.int32, device=dev)}
     gathered = None
-    width = pat.n + pat.p + 2 * pat.m + 2  # x | y | z | s | flag | iterations (apf_quadruped_b200/shard.py)
+    # what the north star gathers: the primal solutions x (what the controller reads, main.cpp:1663), exit
+    # flags and iteration counts; the duals y, z, s stay on the rank that computed them (shard.gather moves
+    # all of x | y | z | s | flag | iterations when a caller wants them)
+    width = pat.n + 2
     if world > 1:
         gathered = torch.empty((world * B, width), dtype=torch.float64, device=dev)
 
@@ -194,7 +200,7 @@ def main():
                             ptr(dout["x"]), ptr(dout["y"]) if pat.p else None, ptr(dout["z"]), ptr(dout["s"]), ptr(dout["flag"]), ptr(dout["iters"]),
                             None, None, st)
         if world > 1:  # the only collective on the path: gather solutions + exit flags + iteration counts
-            packed = torch.cat([dout["x"], dout["y"][:, :pat.p], dout["z"], dout["s"], dout["flag"].double()[:, None], dout["iters"].double()[:, None]], dim=1)
+            packed = torch.cat([dout["x"], dout["flag"].double()[:, None], dout["iters"].double()[:, None]], dim=1)
             dist.all_gather_into_tensor(gathered, packed)
 
     def sync_all():
@@ -206,8 +212,11 @@ def main():
     for _ in range(max(args.warmup, 3)):
         device_step()
     sync_all()
+    # nvidia-smi takes a driver-wide lock: eight ranks polling it five times a second stall each other's
+    # launches (measured: 193 ms instead of 75 ms per step), so only rank 0 samples, twice a second
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -242,7 +251,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(t.item())
-    clocks = sampler.summary()
+    clocks = sampler.summary() if rank == 0 else None
     h2d = 8 * B * (pat.nnzP + pat.nnzA + pat.nnzG + pat.n + pat.m + pat.p)
     d2h = 8 * B * (pat.n + pat.p + 2 * pat.m) + 8 * B
 

@@ -77,3 +77,21 @@ def test_stream_and_latency_kernels_agree_at_default_threshold(qps, oracle):
     for k in ("x", "y", "z", "s", "flag", "iters"):
         assert np.array_equal(out2[k], out[k][:512])
     solver.close()
+
+
+@pytest.mark.parametrize("spill", ["32", "0", "5"])
+def test_stragglers_are_handed_to_the_latency_kernel(qps, oracle, stream_only, monkeypatch, spill):
+    """trot instance 264420 runs into maxit = 100; the throughput kernel hands QPs that exceed
+    QPB_STREAM_SPILL iterations to the latency kernel (second launch), which must not change a bit.
+    spill = 5 sends most of the batch through the hand-over, 0 disables it."""
+    monkeypatch.setenv("QPB_STREAM_SPILL", spill)
+    batch = dogbot.generate("trot", 256, start=264320)
+    solver = qps.BatchSolver(batch.pattern, 256)
+    out = solver.solve(batch)
+    assert solver.last_kernel == "stream" and solver.last_launches == (1 if spill == "0" else 2)
+    ref = oracle.solve_batch(batch)
+    assert ref["flag"][100] == qps.QP_MAXIT and ref["iters"][100] == 100
+    check_against_oracle(out, ref)
+    fval, stat = solver.read_stats(256)
+    assert np.array_equal(fval, ref["fval"])
+    solver.close()
