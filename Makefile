@@ -1,5 +1,6 @@
 # Builds libqpswift_b200.so (host C++ + sm_100a CUDA) in-tree, plus the test oracles.
-#   make            -> apf_quadruped_b200/lib/libqpswift_b200.so, oracle port, oracle/_ref (if reference present)
+#   make            -> apf_quadruped_b200/lib/libqpswift_b200.so (incl. the pattern-specialised kernels generated into
+#                      build/gen by apf_quadruped_b200/codegen.py), oracle port, oracle/_ref (if reference present)
 # -fmad=false is part of the numerical contract (bit-exact with the reference's x86-64 arithmetic).
 NVCC     ?= /usr/local/cuda/bin/nvcc
 CXX      ?= g++
@@ -14,8 +15,20 @@ HOST_SRCS := $(SRC)/amd_order.cpp $(SRC)/symbolic.cpp $(SRC)/program.cpp $(SRC)/
 HOST_OBJS := $(patsubst $(SRC)/%.cpp,$(OBJ)/%.o,$(HOST_SRCS))
 CU_SRCS   := $(SRC)/batch.cu
 CU_OBJS   := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(CU_SRCS))
+# pattern-specialised throughput kernels: `make gen` (needs the library itself, so it is a second
+# pass: make && make gen && make) writes build/gen/stream_gen_<kind>.cu with apf_quadruped_b200/codegen.py
+GEN       := build/gen
+GEN_KINDS ?= trot stance crawl
+GEN_SRCS  := $(wildcard $(GEN)/*.cu)
+GEN_OBJS  := $(patsubst $(GEN)/%.cu,$(OBJ)/gen_%.cu.o,$(GEN_SRCS))
 
-all: $(LIB) oracle
+# Two passes: the generator needs the library's host side (plan + micro-programs), and the generated
+# translation units are then compiled into the same library.
+all:
+	$(MAKE) $(LIB)
+	$(MAKE) gen
+	$(MAKE) $(LIB)
+	$(MAKE) oracle
 
 $(OBJ)/%.o: $(SRC)/%.cpp $(wildcard $(SRC)/*.h) $(wildcard include/*.h include/qpSWIFT/*.h)
 	@mkdir -p $(OBJ)
@@ -25,7 +38,14 @@ $(OBJ)/%.cu.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h $(SRC)/*.cuh) $(wildcard includ
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJ)/$*.ptxas.log || (cat $(OBJ)/$*.ptxas.log; false)
 
-$(LIB): $(HOST_OBJS) $(CU_OBJS)
+$(OBJ)/gen_%.cu.o: $(GEN)/%.cu $(wildcard $(SRC)/*.h $(SRC)/*.cuh) $(wildcard include/*.h include/qpSWIFT/*.h)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJ)/gen_$*.ptxas.log || (tail -50 $(OBJ)/gen_$*.ptxas.log; false)
+
+gen:
+	python -m apf_quadruped_b200.codegen --out $(GEN) $(GEN_KINDS)
+
+$(LIB): $(HOST_OBJS) $(CU_OBJS) $(GEN_OBJS)
 	@mkdir -p $(dir $(LIB))
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart shared
 
@@ -36,4 +56,4 @@ clean:
 	rm -rf build $(LIB)
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean gen

@@ -14,6 +14,7 @@
 #include "capi_internal.h"
 #include "kernels.cuh"
 #include "stream.cuh"
+#include "stream_gen.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -22,10 +23,35 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 namespace qpb {
 
 static thread_local std::string g_last_error;
+
+// Pattern-specialised kernels compiled into the library (stream_gen.cuh): filled by static
+// initialisers of the generated translation units, read by batch_alloc.
+static std::vector<GeneratedKernel> &generated_kernels()
+{
+	static std::vector<GeneratedKernel> v;
+	return v;
+}
+void register_generated_kernel(unsigned long long key, const void *kernel, const char *name)
+{
+	generated_kernels().push_back(GeneratedKernel{key, kernel, name});
+}
+const GeneratedKernel *find_generated_kernel(unsigned long long key)
+{
+	for (const GeneratedKernel &k : generated_kernels())
+		if (k.key == key) return &k;
+	return nullptr;
+}
+int list_generated_kernels(unsigned long long *keys, int capacity)
+{
+	const std::vector<GeneratedKernel> &v = generated_kernels();
+	for (int i = 0; i < (int)v.size() && i < capacity; ++i) keys[i] = v[i].key;
+	return (int)v.size();
+}
 
 static int fail(int code, const char *what, cudaError_t e)
 {
@@ -250,6 +276,7 @@ struct QPBatch
 	int stream_warps = 0;   // warps per CTA (0: the pattern cannot use the throughput kernel)
 	long stream_slots = 0;  // warps in flight on the device = tiles of 32 slices in the workspace
 	long stream_min = 0;    // smallest batch that goes to the throughput kernel
+	const GeneratedKernel *generated = nullptr; // the pattern's specialised kernel, if the library carries one
 	size_t smem_limit = 0;
 	// device staging for the host-pointer entry point
 	double *d_in[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -260,7 +287,7 @@ struct QPBatch
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	double last_kernel_ms = 0.0;
 	long last_launches = 0;
-	int last_kernel = 0; // 0 latency kernel (one QP per warp), 1 throughput kernel (one QP per thread)
+	int last_kernel = 0; // 0 latency kernel (one QP per warp), 1 throughput kernel (one QP per thread), 2 the same, pattern-specialised
 	std::mutex lock;
 };
 
@@ -301,11 +328,13 @@ static int batch_alloc(QPBatch *B)
 	}
 	if (B->stream_warps > 0) {
 		const StreamProgram &sp = B->sprog;
-		CUDA_TRY(cudaFuncSetAttribute(qp_solve_stream_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
-		CUDA_TRY(cudaFuncSetAttribute(qp_solve_stream_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
+		CUDA_TRY(cudaFuncSetAttribute(qp_solve_stream_kernel<InterpretedProgram<4>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
+		CUDA_TRY(cudaFuncSetAttribute(qp_solve_stream_kernel<InterpretedProgram<8>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
 		CUDA_TRY(cudaMalloc(&B->d_stream, sp.words.size() * sizeof(uint64_t)));
 		CUDA_TRY(cudaMemcpy(B->d_stream, sp.words.data(), sp.words.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
 		B->sview.words = B->d_stream;
+		if (!getenv("QPB_STREAM_INTERPRET")) B->generated = find_generated_kernel(stream_program_key(sp));
+		if (B->generated) CUDA_TRY(cudaFuncSetAttribute(B->generated->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
 		for (int s = 0; s < SSEG_COUNT; ++s) { B->sview.first[s] = sp.seg[s].first; B->sview.groups[s] = sp.seg[s].groups; }
 		const long full = (long)B->sm_count * B->stream_warps;
 		B->stream_slots = std::min(full, (B->capacity + 31) / 32);
@@ -382,12 +411,18 @@ static int launch_stream(QPBatch *B, BatchIO io, SolveParams prm, cudaStream_t s
 		io.spill = B->d_spill;
 		io.spill_count = spill_count;
 	}
-	if (sp.group == 4) qp_solve_stream_kernel<4><<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->sview, sp.lay, dm, io, prm, B->d_workspace, (int)slots, B->d_counter);
-	else if (sp.group == 8) qp_solve_stream_kernel<8><<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->sview, sp.lay, dm, io, prm, B->d_workspace, (int)slots, B->d_counter);
+	if (B->generated) {
+		int nslots = (int)slots;
+		double *ws = B->d_workspace;
+		int *ctr = B->d_counter;
+		void *args[] = {&B->sview, const_cast<StreamLayout *>(&sp.lay), &dm, &io, &prm, &ws, &nslots, &ctr};
+		CUDA_TRY(cudaLaunchKernel(B->generated->kernel, dim3((unsigned)grid), dim3((unsigned)warps * 32), args, smem, st));
+	} else if (sp.group == 4) qp_solve_stream_kernel<InterpretedProgram<4>><<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->sview, sp.lay, dm, io, prm, B->d_workspace, (int)slots, B->d_counter);
+	else if (sp.group == 8) qp_solve_stream_kernel<InterpretedProgram<8>><<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->sview, sp.lay, dm, io, prm, B->d_workspace, (int)slots, B->d_counter);
 	else return fail(QPB_E_ARG, "stream program: unsupported group size", cudaSuccess);
 	CUDA_TRY(cudaGetLastError());
 	B->last_launches = 1;
-	B->last_kernel = 1;
+	B->last_kernel = B->generated ? 2 : 1;
 	if (prm.spill_after) { // the stragglers: how many is only known on the device, so the launch is sized for "a few per SM"
 		io.index = B->d_spill;
 		io.count_ptr = spill_count;
@@ -543,6 +578,7 @@ qp_int QPB_BATCH_SET_SIGMA_D(QPBatch *B, qp_real sigma_d)
 double QPB_BATCH_LAST_KERNEL_MS(const QPBatch *B) { return B ? B->last_kernel_ms : 0.0; }
 qp_int QPB_BATCH_LAST_LAUNCHES(const QPBatch *B) { return B ? B->last_launches : 0; }
 int QPB_BATCH_LAST_KERNEL(const QPBatch *B) { return B ? B->last_kernel : -1; }
+qp_int QPB_GENERATED_KERNELS(unsigned long long *keys, int capacity) { return list_generated_kernels(keys, keys ? capacity : 0); }
 
 // Host access to fval / stat of the last host-pointer solve (used by QP_SOLVE to fill `stats`).
 qp_int QPB_BATCH_READ_STATS(QPBatch *B, qp_int count, qp_real *fval, qp_real *stat)

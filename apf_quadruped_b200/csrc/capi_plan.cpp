@@ -107,6 +107,8 @@ const unsigned long long *QPB_PLAN_STREAM(const QPBPlan *h, qp_int *words)
 	return reinterpret_cast<const unsigned long long *>(h->stream.words.data());
 }
 
+unsigned long long QPB_PLAN_STREAM_KEY(const QPBPlan *h) { return stream_program_key(h->stream); }
+
 qp_int QPB_PLAN_STREAM_INFO(const QPBPlan *h, long long *out, int capacity)
 {
 	std::vector<long long> v;

@@ -140,14 +140,14 @@ __device__ __forceinline__ void sts64(unsigned addr, double v)
 
 // One slot of a quotient / ordered-sum super-wave.  Rare (a few dozen per factorisation) and long
 // (an FP64 division is ~20 dependent instructions), so they are real calls, not inlined copies.
-__device__ __noinline__ void quotient_slot(const unsigned lo, const unsigned hi, const unsigned sb)
+static __device__ __noinline__ void quotient_slot(const unsigned lo, const unsigned hi, const unsigned sb)
 {
 	const unsigned M = (1u << INS_ADDR_BITS) - 1u;
 	// the divisor is a pivot: dynamic regularisation (ldl.c:319-320) applied on use
 	if (hi & 0x8000u) sts64(sb + (((hi >> 16) & M) << 3), lds64(sb + ((lo & M) << 3)) / regularise(lds64(sb + ((hi & M) << 3))));
 }
 
-__device__ __noinline__ void ordered_sum_slot(const unsigned lo, const unsigned hi, const unsigned sb)
+static __device__ __noinline__ void ordered_sum_slot(const unsigned lo, const unsigned hi, const unsigned sb)
 {
 	const unsigned M = (1u << INS_ADDR_BITS) - 1u;
 	const int cnt = (hi & 0x8000u) ? (int)(hi & M) : 0;

@@ -80,7 +80,7 @@ __device__ __forceinline__ uint4 decode_word(const uint2 w)
 // One micro-op of a SLOW group (quotients, pivots, copies, late operands).  A real call: slow groups
 // are a small share of the work and the interpreter has to stay small enough for the instruction cache.
 template <bool GS>
-__device__ __noinline__ double2 slow_op(const unsigned f1, const unsigned f2, const unsigned c, const unsigned fl, double P, double t, double d, char *g, const unsigned sb)
+static __device__ __noinline__ double2 slow_op(const unsigned f1, const unsigned f2, const unsigned c, const unsigned fl, double P, double t, double d, char *g, const unsigned sb)
 {
 	const unsigned op = fl & 15u;
 	if (fl & LO(SF_LATE1)) P = *reinterpret_cast<const double *>(g + f1);
@@ -160,7 +160,7 @@ __device__ __forceinline__ void execute(const uint4 chunk, const int first, cons
 // ngroups is a multiple of DEPTH (the compiler pads); the program is followed by 4 chunks of padding.
 // DEPTH = groups per chunk = operand buffers.
 template <int G, bool GS, int DEPTH>
-__device__ __noinline__ void run_stream(const uint2 *__restrict__ prog, const int ngroups, double *slice, const unsigned sb)
+static __device__ __noinline__ void run_stream(const uint2 *__restrict__ prog, const int ngroups, double *slice, const unsigned sb)
 {
 	constexpr int CH = DEPTH * G; // micro-ops per chunk, one per lane (lanes beyond CH idle along)
 	static_assert(CH <= 32, "a chunk is at most one micro-op per lane");
@@ -190,7 +190,7 @@ __device__ __noinline__ void run_stream(const uint2 *__restrict__ prog, const in
 
 // Sequential inner product sum_i a[i]*b[i] from 0.0 in ascending order (norm Auxilary.c:430-440,
 // innerproduct 451-462); the loads and products of eight terms are issued together.
-__device__ __noinline__ double stream_dot(const double *a, const double *b, const int count)
+static __device__ __noinline__ double stream_dot(const double *a, const double *b, const int count)
 {
 	double acc = 0.0;
 	for (int i0 = 0; i0 < count; i0 += 8) {
@@ -210,8 +210,8 @@ __device__ __noinline__ double stream_dot(const double *a, const double *b, cons
 
 // Out of line on purpose: an inlined FP64 division / square root is ~30 instructions, and the elementwise
 // steps below are unrolled eight-fold; the kernel has to stay friendly to the instruction cache.
-__device__ __noinline__ double div_rn(const double a, const double b) { return a / b; }
-__device__ __noinline__ double sqrt_rn(const double a) { return sqrt(a); }
+static __device__ __noinline__ double div_rn(const double a, const double b) { return a / b; }
+static __device__ __noinline__ double sqrt_rn(const double a) { return sqrt(a); }
 
 enum { SM_IDLE = 0, SM_INIT = 1, SM_PRED = 2, SM_CENT = 3 };
 static const int STREAM_MAX_WARPS = 8;
@@ -233,25 +233,53 @@ static const int STREAM_U = 8; // elements of an elementwise step whose loads ar
 		}                                                              \
 	}
 
+// Where the four micro-programs come from.  InterpretedProgram<G>: the words are fetched from memory
+// and interpreted (run_stream above), whatever the pattern.  A GENERATED program (stream_gen.cuh,
+// apf_quadruped_b200/codegen.py) is the same micro-op sequence of one particular pattern compiled into
+// straight-line code; the kernel around the programs is the same.
 template <int G>
+struct InterpretedProgram
+{
+	static constexpr bool cta_sync = false; // the warps of a CTA never wait for one another
+	static __device__ __forceinline__ void factor(const StreamView &sv, double *slice, const unsigned sb, bool) { run_stream<G, false, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_FACTOR], sv.groups[SSEG_FACTOR], slice, sb); }
+	static __device__ __forceinline__ void solve(const StreamView &sv, double *slice, const unsigned sb, bool) { run_stream<G, false, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], slice, sb); }
+	static __device__ __forceinline__ void resid(const StreamView &sv, double *slice, const unsigned sb, bool) { run_stream<G, true, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_RESID], sv.groups[SSEG_RESID], slice, sb); }
+	static __device__ __forceinline__ void resz(const StreamView &sv, double *slice, const unsigned sb, bool) { run_stream<G, true, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_RESZ], sv.groups[SSEG_RESZ], slice, sb); }
+};
+
+// Does any lane want this step?  A program with cta_sync = true (generated straight-line code, which
+// is far larger than the instruction caches) keeps the warps of its CTA walking the same code at the
+// same time: the question is then put to the whole CTA, every warp enters the step (and meets the
+// others at the barriers inside it), and a warp none of whose lanes wants it skips the work.
+template <class PROG>
+__device__ __forceinline__ bool any_wants(const bool mine)
+{
+	if (PROG::cta_sync) return __syncthreads_or(mine) != 0;
+	return __any_sync(0xffffffffu, mine) != 0;
+}
+
+template <class PROG>
 __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kernel(const StreamView sv, const StreamLayout L, const StreamDims dm, const BatchIO io, const SolveParams prm, double *workspace, const int nslots, int *__restrict__ counter)
 {
 	extern __shared__ __align__(16) double smem[];
 	const unsigned FULL = 0xffffffffu;
 	const int lane = lane_id(), warp = threadIdx.x >> 5;
 	const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
-	if (slot >= nslots) return; // warps never wait for one another
+	const bool live = slot < nslots;
+	if (!live && !PROG::cta_sync) return; // (with cta_sync a warp without a tile keeps the CTA's barriers company)
 	double *tile = workspace + (size_t)slot * L.total * 32; // the warp's 32 interleaved slices
 	double *g = tile + lane;
 	const unsigned sb = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)(warp * L.scratch * 32 + lane) * 8u;
 	const int n = dm.n, m = dm.m, p = dm.p, np = dm.n + dm.p, N = dm.N;
 	const double thr = prm.reltol / sqrt(3.0);
-	SL(L.zero) = 0.0;
-	SL(L.one) = 1.0;
-	SL(L.mone) = -1.0;
+	if (live) {
+		SL(L.zero) = 0.0;
+		SL(L.one) = 1.0;
+		SL(L.mone) = -1.0;
+	}
 
 	int q = -1, iters = 0;
-	bool active = false, exhausted = false;
+	bool active = false, exhausted = !live;
 	double sigma = 0.0, mu = 0.0, ap = 0.0, ad = 0.0;
 	Scalars sc;
 	sc.n_rx = sc.n_ry = sc.n_rz = sc.n_mu = sc.fval = 0.0;
@@ -263,13 +291,14 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 		if (active && iters >= prm.maxit) flag = 2; // QP_MAXIT (qpSWIFT.c:604-607)
 		else if (active && prm.spill_after && iters >= prm.spill_after) flag = 4; // a straggler: the latency kernel takes it (batch.cu)
 		const bool need_res = active && flag < 0;
-		if (__any_sync(FULL, need_res)) {
+		if (any_wants<PROG>(need_res)) {
+			const bool mine = __any_sync(FULL, need_res);
 			if (need_res) { // s - h (= -(h - s), exactly), and x | y | z into the window for the residual program
 				STREAM_FOR(m, a8[j] = SL(L.h + i); b8[j] = SL(L.s + i); c8[j] = SL(L.z + i);, SL(L.hs + i) = b8[j] - a8[j]; sts64(sb + ((unsigned)(np + i) << 8), c8[j]);)
 				STREAM_FOR(n, a8[j] = SL(L.x + i);, sts64(sb + ((unsigned)i << 8), a8[j]);)
 				STREAM_FOR(p, a8[j] = SL(L.y + i);, sts64(sb + ((unsigned)(n + i) << 8), a8[j]);)
 			}
-			run_stream<G, true, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_RESID], sv.groups[SSEG_RESID], g, sb);
+			PROG::resid(sv, g, sb, mine);
 			if (need_res) {
 				sc.n_rx = sqrt(stream_dot(g + (L.r << 5), g + (L.r << 5), n));
 				if (p) sc.n_ry = sqrt(stream_dot(g + ((L.r + n) << 5), g + ((L.r + n) << 5), p));
@@ -367,19 +396,21 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 			           SL(L.rhs + np + i) = c8[j] - div_rn(ds, b8[j]);)
 			STREAM_FOR(np, a8[j] = SL(L.r + i);, SL(L.rhs + i) = a8[j];)
 		}
-		if (!__any_sync(FULL, mode != SM_IDLE)) break;
+		if (!any_wants<PROG>(mode != SM_IDLE)) break;
+		const bool busy = __any_sync(FULL, mode != SM_IDLE);
 
-		run_stream<G, false, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_FACTOR], sv.groups[SSEG_FACTOR], g, sb);
-		run_stream<G, false, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], g, sb);
+		PROG::factor(sv, g, sb, busy);
+		PROG::solve(sv, g, sb, busy);
 
 		// ---- kkt_initialize, second half (Auxilary.c:1044-1083) ------------------------------------------
-		if (__any_sync(FULL, mode == SM_INIT)) {
+		if (any_wants<PROG>(mode == SM_INIT)) {
+			const bool mine = __any_sync(FULL, mode == SM_INIT);
 			if (mode == SM_INIT) {
 				STREAM_FOR(n, a8[j] = SL(L.rhs + i);, SL(L.x + i) = a8[j]; sts64(sb + ((unsigned)i << 8), a8[j]);) // x also into the window
 				STREAM_FOR(p, a8[j] = SL(L.rhs + n + i);, SL(L.y + i) = a8[j];)
 				STREAM_FOR(m, a8[j] = SL(L.h + i);, SL(L.hs + i) = -a8[j];)
 			}
-			run_stream<G, true, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_RESZ], sv.groups[SSEG_RESZ], g, sb); // hs <- -(G x) - (-h) = h - G x
+			PROG::resz(sv, g, sb, mine); // hs <- -(G x) - (-h) = h - G x
 			if (mode == SM_INIT) {
 				const double inf = __longlong_as_double(0x7ff0000000000000LL);
 				double lo = inf, hi = -inf;
@@ -427,8 +458,8 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 			           SL(L.rhs + np + i) = e8[j] - div_rn(ds, d8[j]);)
 			STREAM_FOR(np, a8[j] = SL(L.r + i);, SL(L.rhs + i) = a8[j];)
 		}
-		if (__any_sync(FULL, mode == SM_PRED)) {
-			run_stream<G, false, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], g, sb);
+		if (any_wants<PROG>(mode == SM_PRED)) {
+			PROG::solve(sv, g, sb, __any_sync(FULL, mode == SM_PRED));
 			if (mode == SM_PRED) step(true);
 		}
 		(void)N;

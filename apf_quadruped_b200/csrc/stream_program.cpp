@@ -322,4 +322,16 @@ bool build_stream_program(const Plan &pl, StreamProgram &prog, int group)
 	return true;
 }
 
+uint64_t stream_program_key(const StreamProgram &prog)
+{
+	uint64_t h = 1469598103934665603ull;
+	auto mix = [&](uint64_t v) { h ^= v; h *= 1099511628211ull; };
+	const int32_t *lay = reinterpret_cast<const int32_t *>(&prog.lay);
+	for (size_t i = 0; i < sizeof(StreamLayout) / sizeof(int32_t); ++i) mix((uint64_t)(uint32_t)lay[i]);
+	mix((uint64_t)prog.group);
+	for (int s = 0; s < SSEG_COUNT; ++s) { mix((uint64_t)prog.seg[s].first); mix((uint64_t)prog.seg[s].groups); }
+	for (uint64_t w : prog.words) mix(w);
+	return h;
+}
+
 } // namespace qpb

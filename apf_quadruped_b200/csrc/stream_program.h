@@ -102,6 +102,10 @@ struct StreamProgram
 
 bool build_stream_program(const Plan &plan, StreamProgram &prog, int group = 8);
 
+// FNV-1a over the layout and the words: the name under which a pattern-specialised kernel generated
+// from this very program (apf_quadruped_b200/codegen.py) registers itself (stream_gen.cuh).
+uint64_t stream_program_key(const StreamProgram &prog);
+
 } // namespace qpb
 
 #endif

@@ -59,7 +59,7 @@ class QP(C.Structure):
 EXPORTS = [
     "QP_SETUP", "QP_SETUP_dense", "QP_SOLVE", "QP_CLEANUP", "QP_CLEANUP_dense",
     "QPB_PLAN_CREATE", "QPB_PLAN_DESTROY", "QPB_PLAN_ARRAY", "QPB_PLAN_INFO", "QPB_AMD_ORDER", "QPB_PLAN_PROGRAM",
-    "QPB_PLAN_LAYOUT", "QPB_PLAN_STREAM", "QPB_PLAN_STREAM_INFO",
+    "QPB_PLAN_LAYOUT", "QPB_PLAN_STREAM", "QPB_PLAN_STREAM_INFO", "QPB_PLAN_STREAM_KEY", "QPB_GENERATED_KERNELS",
     "QP_SETUP_BATCH", "QPB_BATCH_CREATE", "QP_SOLVE_BATCH", "QP_SOLVE_BATCH_DEVICE", "QP_CLEANUP_BATCH",
     "QPB_BATCH_READ_STATS", "QPB_BATCH_SET_SIGMA_D", "QPB_BATCH_LAST_KERNEL_MS", "QPB_BATCH_LAST_LAUNCHES", "QPB_BATCH_LAST_KERNEL",
     "QPB_LDL_NUMERIC_BATCH", "QPB_LDL_SOLVE_BATCH", "QPB_LAST_ERROR", "QPB_DEVICE_COUNT",
@@ -99,6 +99,10 @@ def lib():
         lb.QPB_PLAN_STREAM.argtypes = [V, PL]
         lb.QPB_PLAN_STREAM_INFO.restype = L
         lb.QPB_PLAN_STREAM_INFO.argtypes = [V, C.POINTER(C.c_longlong), C.c_int]
+        lb.QPB_PLAN_STREAM_KEY.restype = C.c_uint64
+        lb.QPB_PLAN_STREAM_KEY.argtypes = [V]
+        lb.QPB_GENERATED_KERNELS.restype = L
+        lb.QPB_GENERATED_KERNELS.argtypes = [C.POINTER(C.c_uint64), C.c_int]
         lb.QPB_AMD_ORDER.restype = L
         lb.QPB_AMD_ORDER.argtypes = [L, PL, PL, PL]
         lb.QP_SETUP_BATCH.restype = V
@@ -236,6 +240,10 @@ class Plan:
             info["segments"][name] = {k: int(buf[base + i]) for i, k in enumerate(self.STREAM_STATS)}
         return info
 
+    def stream_key(self) -> int:
+        """Key of the micro-programs: a kernel generated from them (codegen.py) registers under it."""
+        return int(lib().QPB_PLAN_STREAM_KEY(self.handle))
+
     def stream_words(self, which: str | None = None) -> np.ndarray:
         cnt = C.c_long()
         ptr = lib().QPB_PLAN_STREAM(self.handle, C.byref(cnt))
@@ -319,7 +327,12 @@ class BatchSolver:
 
     @property
     def last_kernel(self) -> str:
-        return {0: "warp", 1: "stream"}.get(int(lib().QPB_BATCH_LAST_KERNEL(self.handle)), "?")
+        return {0: "warp", 1: "stream", 2: "stream"}.get(int(lib().QPB_BATCH_LAST_KERNEL(self.handle)), "?")
+
+    @property
+    def last_kernel_generated(self) -> bool:
+        """The throughput kernel that ran was the pattern-specialised one (codegen.py), not the interpreter."""
+        return int(lib().QPB_BATCH_LAST_KERNEL(self.handle)) == 2
 
     @property
     def last_launches(self) -> int:

@@ -89,6 +89,11 @@ qp_int QPB_PLAN_LAYOUT(const QPBPlan *plan, int *out, int capacity);
  * Exposed so that the programs can be checked on the host (tests/test_stream_program.py). */
 const unsigned long long *QPB_PLAN_STREAM(const QPBPlan *plan, qp_int *words);
 qp_int QPB_PLAN_STREAM_INFO(const QPBPlan *plan, long long *out, int capacity);
+/* FNV-1a of the micro-programs and their layout: the name under which a kernel specialised for this
+ * pattern (generated from these words by apf_quadruped_b200/codegen.py, compiled into the library) is
+ * registered.  QPB_GENERATED_KERNELS: how many such kernels the library carries; keys[i] for i < capacity. */
+unsigned long long QPB_PLAN_STREAM_KEY(const QPBPlan *plan);
+qp_int QPB_GENERATED_KERNELS(unsigned long long *keys, int capacity);
 
 /* The ordering alone (test hook for amd_l_order, amd_order.c:21-199): returns the AMD status
  * (0 ok, 1 ok-but-jumbled, -2 invalid) and writes Perm[n]. */
@@ -135,7 +140,9 @@ double QPB_BATCH_LAST_KERNEL_MS(const QPBatch *batch);
 qp_int QPB_BATCH_LAST_LAUNCHES(const QPBatch *batch);
 /* Which kernel the last solve used: 0 = latency kernel (one QP per warp, working set in shared
  * memory; small batches), 1 = throughput kernel (one QP per thread, working sets interleaved in HBM;
- * batches of at least QPB_STREAM_MIN [default 2048] QPs). */
+ * batches of at least QPB_STREAM_MIN [default 2048] QPs) interpreting the pattern's micro-programs,
+ * 2 = the throughput kernel specialised for the pattern (micro-programs compiled into straight-line
+ * code, see QPB_PLAN_STREAM_KEY). */
 int QPB_BATCH_LAST_KERNEL(const QPBatch *batch);
 
 /* ---------------------------------------------------------------------------------------------

@@ -10,5 +10,5 @@ $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 CMD2="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-kernels"
 $CMD2 > gpurun_out/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:qp_solve -s 3 -c 1 -o gpurun_out/prof_$TAG -f $CMD2 > gpurun_out/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:${KERNEL:-qp_solve_stream} -s 3 -c 1 -o gpurun_out/prof_$TAG -f $CMD2 > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -c 600 gpurun_out/bench_$TAG.json

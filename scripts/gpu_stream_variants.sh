@@ -13,7 +13,7 @@ for kind in os.environ.get('KINDS','trot').split(','):
     best = 1e9
     for rep in range(3):
         out = s.solve(b); best = min(best, s.last_kernel_ms)
-    print('RESULT', kind, cnt, s.last_kernel, '%.0f solves/s' % (cnt / best * 1e3), 'iters', out['iters'].sum(), 'flags', np.bincount(out['flag']), flush=True)
+    print('RESULT', kind, cnt, s.last_kernel, 'generated' if s.last_kernel_generated else 'interpreted', '%.0f solves/s' % (cnt / best * 1e3), 'iters', out['iters'].sum(), 'flags', np.bincount(out['flag']), flush=True)
     s.close()
 PY
 done

@@ -22,13 +22,20 @@ def stream_only(monkeypatch):
     monkeypatch.setenv("QPB_STREAM_MIN_WARPS", "1")  # also patterns that would default to the latency kernel (mpc)
 
 
+GENERATED_KINDS = ("trot", "stance", "crawl")  # Makefile: GEN_KINDS
+
+
+@pytest.mark.parametrize("program", ["generated", "interpreted"])
 @pytest.mark.parametrize("kind,count", [("stance", 300), ("crawl", 97), ("trot", 300), ("mpc", 70)])
-def test_stream_batch_matches_oracle(qps, oracle, stream_only, kind, count):
+def test_stream_batch_matches_oracle(qps, oracle, stream_only, monkeypatch, kind, count, program):
     """ragged counts: partial warps, lanes that run out of work at different times"""
+    if program == "interpreted":
+        monkeypatch.setenv("QPB_STREAM_INTERPRET", "1")
     batch = dogbot.generate(kind, count, start=40000)
     solver = qps.BatchSolver(batch.pattern, count)
     out = solver.solve(batch)
     assert solver.last_kernel == "stream"
+    assert solver.last_kernel_generated == (program == "generated" and kind in GENERATED_KINDS)
     ref = oracle.solve_batch(batch)
     check_against_oracle(out, ref)
     fval, stat = solver.read_stats(count)
@@ -62,13 +69,30 @@ def test_stream_user_permutation_and_sigma_d(qps, oracle, stream_only):
     solver.close()
 
 
+def test_generated_and_interpreted_programs_agree_on_a_full_device(qps, stream_only, monkeypatch):
+    """40,000 trot QPs: every warp of every SM busy, lanes refilled from the queue; the specialised
+    kernel and the interpreter must agree bit for bit (the oracle checks smaller batches above)."""
+    batch = dogbot.generate("trot", 40000, start=123456)
+    solver = qps.BatchSolver(batch.pattern, batch.count)
+    out = solver.solve(batch)
+    assert solver.last_kernel_generated
+    solver.close()
+    monkeypatch.setenv("QPB_STREAM_INTERPRET", "1")
+    solver = qps.BatchSolver(batch.pattern, batch.count)
+    out2 = solver.solve(batch)
+    assert solver.last_kernel == "stream" and not solver.last_kernel_generated
+    for k in ("x", "y", "z", "s", "flag", "iters"):
+        assert np.array_equal(out2[k], out[k]), k
+    solver.close()
+
+
 def test_stream_and_latency_kernels_agree_at_default_threshold(qps, oracle):
     """4,096 trot QPs go to the throughput kernel by default; 512 of them to the latency kernel;
     both are bit-identical with the oracle, so results do not depend on how a batch is cut."""
     batch = dogbot.generate("trot", 4096, start=70000)
     solver = qps.BatchSolver(batch.pattern, 4096)
     out = solver.solve(batch)
-    assert solver.last_kernel == "stream"
+    assert solver.last_kernel == "stream" and solver.last_kernel_generated
     ref, _ = oracle.run_batch(batch)
     check_against_oracle(out, ref)
     small = dogbot.generate("trot", 512, start=70000)
