@@ -4,10 +4,26 @@ straight-line CUDA.
 The interpreter of csrc/stream.cuh spends ~20 instructions per micro-op on instruction supply (shuffles,
 flag tests, address arithmetic); for a KNOWN sparsity pattern every index and every flag is a constant,
 so the same micro-op sequence can be emitted as source: one `ld.global` with an immediate offset, one
-`ld.shared` with an immediate offset, one multiply and one subtract per term.  The arithmetic (and its
-order) is the program's, word for word -- the programs themselves are checked against the reference on
-the host (tests/test_stream_program.py) -- so the generated kernels stay bit-identical with reference
-qpSWIFT (ldl.c:253-326 LDL_numeric, 495-597 the solves, Auxilary.c:745-786 computeresiduals).
+multiply and one subtract per term.  The arithmetic of every number (which operands, in which order) is
+the program's, word for word -- the programs themselves are checked against the reference on the host
+(tests/test_stream_program.py) -- so the generated kernels stay bit-identical with reference qpSWIFT
+(ldl.c:253-326 LDL_numeric, 495-597 the solves, Auxilary.c:745-786 computeresiduals).  What the generator
+is free to choose, and chooses for the memory system, is WHEN independent numbers are computed and
+WHERE a value waits for its next use:
+
+* HBM operands are requested `dist` micro-ops before they are used (never before the last store to
+  the same element);
+* an operand that was loaded or stored at most `reuse` micro-ops ago is taken from its register instead
+  of HBM; constants (+0.0, 1.0, -1.0) are literals;
+* LDL_numeric: up to `rows` consecutive rows of L are computed TOGETHER (their chains interleaved), so
+  that the entries of L they both read are fetched once; the row-local work vectors Y of these rows
+  live in registers (every index is known) as far as `ybudget` doubles go, and in disjoint parts of
+  the shared-memory window beyond; the quotient L(k,i) = y_i / D_i and the pivot update follow their
+  chain immediately (same operations, same order per number as ldl.c:299-320).
+
+The result is an IR (a list of statements over single-assignment variables) that is printed as CUDA and
+that `evaluate` executes on the host, so the transformation itself is checked against the untransformed
+program bit for bit without a GPU (tests/test_codegen.py).
 
     python -m apf_quadruped_b200.codegen --out build/gen trot stance crawl
 
@@ -20,12 +36,16 @@ from __future__ import annotations
 import argparse
 import os
 
+import numpy as np
+
 TERM, DIVACC, DIV, INITD, ENDD, LOADS, NOP = 0, 2, 3, 4, 5, 6, 8
 FIRSTZ, INIT, ST_SHARED, ST_HBM, LATE1, ONE, SLOW = (1 << (52 + i) for i in range(7))
 
+DEFAULTS = dict(dist=24, reuse=16, chunk=256, rows=3, ybudget=60, fn_ops=400, block_ops=4000, sync=1000000)
+
 
 class Op:
-    __slots__ = ("f1", "f2", "c", "op", "w", "uses_p", "uses_s", "load_at", "name")
+    __slots__ = ("f1", "f2", "c", "op", "w", "uses_p", "uses_s")
 
     def __init__(self, w: int):
         self.w = w
@@ -52,114 +72,478 @@ def live_ops(words, zero):
     return out
 
 
-def schedule_loads(ops, dist, chunk):
-    """Where the HBM operand of each micro-op is requested: `dist` micro-ops ahead, but never before a
-    store to the same element (read-after-write through memory) and never before its chunk starts."""
-    last_store = {}
-    for i, o in enumerate(ops):
-        if o.uses_p:
-            at = max(i - dist, last_store.get(o.f1, -1) + 1, (i // chunk) * chunk)
-            o.load_at = min(at, i)
+# ---------------------------------------------------------------------------------------------------
+# IR.  Statements (tuples) over single-assignment double variables (strings); operands may also be the
+# literals "0.0", "1.0", "-1.0".
+#   ("ldg", v, e)            v = HBM slice[e]                 ("lds", v, e)   v = window[e]
+#   ("stg", e, a)            HBM slice[e] = a                 ("sts", e, a)   window[e] = a
+#   ("msub", v, base, a, b)  v = base - a*b   (b None: v = base - a)
+#   ("div", v, a, b)  v = a / b               ("regu", v, a)  v = regularise(a)  (ldl.c:319-320)
+# A Function is a list of statements; a "carried" one takes the accumulators (t, d) of the program in
+# and hands them on (chains of the program may cross its boundaries).
+# ---------------------------------------------------------------------------------------------------
+class Function:
+    def __init__(self, name, carried, start):
+        self.name = name
+        self.carried = carried  # True: double2 f(g, sb, t, d) returning the accumulators; False: void f(g, sb)
+        self.items = []         # (position in micro-ops, statement)
+        self.loads = []         # (scheduled position, variable, element)
+        self.t = "t_in"
+        self.d = "d_in"
+        self.start = start
+        self.nops = 0
+
+
+class Builder:
+    """Emits the statements of one segment, function by function, with the operand cache."""
+
+    def __init__(self, seg, consts, opt, scratch=0):
+        self.seg = seg
+        self.scratch = scratch       # doubles of shared-memory window per lane
+        self.consts = consts  # element -> literal
+        self.opt = opt
+        self.functions = []
+        self.fn = None
+        self.nvar = 0
+        self.pos = 0                 # micro-ops emitted so far in this segment
+        self.cache = {}              # element -> [variable, position of the last use]
+        self.last_store = {}         # element -> position of the last store
+        self.stats = dict(ops=0, hbm_loads=0, reused=0, lds=0, sts=0, stg=0, functions=0)
+
+    def var(self, prefix="v"):
+        self.nvar += 1
+        return f"{prefix}{self.nvar}"
+
+    def begin(self, carried):
+        self.fn = Function(f"{self.seg}_{len(self.functions)}", carried, self.pos)
+        self.functions.append(self.fn)
+        self.cache = {}  # registers do not survive a call
+        self.stats["functions"] += 1
+
+    def put(self, stmt):
+        self.fn.items.append((self.pos, stmt))
+
+    def operand(self, e):
+        """The value of HBM element e as a variable: literal, cached register, or a (scheduled) load."""
+        if e in self.consts:
+            return self.consts[e]
+        hit = self.cache.get(e)
+        if hit is not None and self.pos - hit[1] <= self.opt["reuse"]:
+            hit[1] = self.pos
+            self.stats["reused"] += 1
+            return hit[0]
+        v = self.var("p")
+        at = max(self.pos - self.opt["dist"], self.last_store.get(e, -1) + 1, self.fn.start)
+        self.fn.loads.append((min(at, self.pos), v, e))
+        self.cache[e] = [v, self.pos]
+        self.stats["hbm_loads"] += 1
+        return v
+
+    def stg(self, e, a):
+        self.put(("stg", e, a))
+        self.last_store[e] = self.pos
+        self.cache[e] = [a, self.pos]
+        self.stats["stg"] += 1
+
+    def lds(self, e):
+        v = self.var("s")
+        self.put(("lds", v, e))
+        self.stats["lds"] += 1
+        return v
+
+    def sts(self, e, a):
+        self.put(("sts", e, a))
+        self.stats["sts"] += 1
+
+    def step(self):
+        self.pos += 1
+        self.fn.nops += 1
+        self.stats["ops"] += 1
+
+    # -- one micro-op with the window in shared memory (the program's own semantics, stream.cuh slow_op) --
+    def generic(self, o):
+        f, w = self.fn, o.w
+        P = self.operand(o.f1) if o.uses_p else None
+        S = self.lds(o.f2) if o.uses_s else None
+        if o.op == TERM:
+            if w & INIT:
+                f.t = P
+            else:
+                v = self.var("t")
+                self.put(("msub", v, "0.0" if w & FIRSTZ else f.t, P, None if w & ONE else S))
+                f.t = v
+        elif o.op == DIVACC:
+            v = self.var("t")
+            self.put(("div", v, S, P))
+            d = self.var("d")
+            self.put(("msub", d, f.d, v, S))
+            f.t, f.d = v, d
+        elif o.op == DIV:
+            v = self.var("t")
+            self.put(("div", v, S, P))
+            f.t = v
+        elif o.op == INITD:
+            f.d = P
+        elif o.op == ENDD:
+            v = self.var("t")
+            self.put(("regu", v, f.d))
+            f.t = v
+        elif o.op == LOADS:
+            f.t = S
+        if w & ST_HBM:
+            self.stg(o.c, f.t)
+        if w & ST_SHARED:
+            self.sts(o.c, f.t)
+        self.step()
+
+    def generic_run(self, ops):
+        """ops in program order, a new function every `chunk` micro-ops, (t, d) carried across."""
+        for o in ops:
+            if self.fn is None or not self.fn.carried or self.fn.nops >= self.opt["chunk"]:
+                self.begin(True)
+            self.generic(o)
+
+
+def parse_rows(ops):
+    """LDL_numeric as stream_program.cpp emits it: per row of L the chains of its pattern (each ends with
+    the store of Y[t] into window slot t), INITD, one DIVACC per pattern entry, ENDD.  None: not that shape."""
+    rows, cur, chain, tail = [], None, [], False
+    for o in ops:
+        if cur is None:
+            cur = dict(chains=[], initd=None, divacc=[], endd=None, ops=0)
+        cur["ops"] += 1
+        if o.op == TERM and not tail:
+            chain.append(o)
+            if o.w & ST_HBM:
+                return None
+            if o.w & ST_SHARED:
+                if o.c != len(cur["chains"]):
+                    return None
+                cur["chains"].append(chain)
+                chain = []
+        elif o.op == INITD and not chain and not tail:
+            cur["initd"], tail = o, True
+        elif o.op == DIVACC and tail and (o.w & ST_HBM) and not (o.w & ST_SHARED) and o.f2 == len(cur["divacc"]):
+            cur["divacc"].append(o)
+        elif o.op == ENDD and tail and (o.w & ST_HBM) and not (o.w & ST_SHARED) and len(cur["divacc"]) == len(cur["chains"]):
+            cur["endd"] = o
+            rows.append(cur)
+            cur, tail = None, False
         else:
-            o.load_at = -1
-        if o.w & ST_HBM:
-            last_store[o.c] = i
+            return None
+    if cur is not None or chain:
+        return None
+    for r in rows:
+        for t, ch in enumerate(r["chains"]):
+            if any(o.uses_s and not o.f2 < t for o in ch):
+                return None
+    return rows
 
 
-def emit_segment(name, words, zero, dist, chunk, out, div="div_inline", attr="__noinline__"):
-    ops = live_ops(words, zero)
-    schedule_loads(ops, dist, chunk)
-    pending = {}  # position -> ops whose operand is requested there
-    for i, o in enumerate(ops):
-        o.name = f"p{i}"
-        if o.uses_p:
-            pending.setdefault(o.load_at, []).append(o)
-    nchunks = (len(ops) + chunk - 1) // chunk
-    for ck in range(nchunks):
-        out.append(f"__device__ {attr} double2 {name}_{ck}(char *g, const unsigned sb, double t, double d)\n{{")
-        for i in range(ck * chunk, min(len(ops), (ck + 1) * chunk)):
-            for o in pending.get(i, ()):
-                out.append(f'\tdouble {o.name}; asm volatile("ld.global.f64 %0, [%1+{o.f1 << 8}];" : "=d"({o.name}) : "l"(g) : "memory");')
-            o = ops[i]
-            w = o.w
-            s = f"s{i}"
-            if o.uses_s:
-                out.append(f'\tdouble {s}; asm volatile("ld.shared.f64 %0, [%1+{o.f2 << 8}];" : "=d"({s}) : "r"(sb));')
-            if o.op == TERM:
-                if w & INIT:
-                    out.append(f"\tt = {o.name};")
+def build_factor(B: Builder, ops):
+    """Row blocks with Y in registers (module docstring); rows that do not fit keep the program's form."""
+    opt = B.opt
+    rows = parse_rows(ops)
+    if rows is None:
+        B.generic_run(ops)
+        return
+    # blocks of consecutive rows; the first rows of a block keep Y in registers while the budget lasts,
+    # the others get their own part of the window
+    k, blocks = 0, []
+    while k < len(rows):
+        blk, regs, smem, nops = [], 0, 0, 0
+        while len(blk) < max(1, opt["rows"]) and k + len(blk) < len(rows):
+            nx = rows[k + len(blk)]
+            n = len(nx["chains"])
+            if blk and nops + nx["ops"] > opt["block_ops"]:
+                break
+            if regs + n <= opt["ybudget"] and not any(c == "smem" for c, _ in blk):
+                blk.append(("regs", 0))
+                regs += n
+            elif smem + n <= B.scratch:
+                blk.append(("smem", smem))
+                smem += n
+            else:
+                break
+            nops += nx["ops"]
+        assert blk, "a row's pattern exceeds the shared-memory window"
+        blocks.append((k, blk))
+        k += len(blk)
+
+    for k0, classes in blocks:
+        blk = list(range(k0, k0 + len(classes)))
+        where = {r: classes[r - k0] for r in blk}
+        if B.fn is None or B.fn.nops >= opt["fn_ops"]:
+            B.begin(False)
+        pending = set()  # elements this block has yet to store: nobody may read them before
+        for r in blk:
+            pending.update(o.c for o in rows[r]["divacc"])
+            pending.add(rows[r]["endd"].c)
+        nxt = {r: 0 for r in blk}
+        dacc, Y, left = {}, {}, list(blk)
+        while left:
+            ready, finished = [], False
+            for r in list(left):
+                R, t = rows[r], nxt[r]
+                if r not in dacc:  # D[k] = Y[k] (ldl.c:299): the diagonal entry of K, or +0.0
+                    dacc[r] = B.operand(R["initd"].f1)
+                    B.step()
+                if t == len(R["chains"]):
+                    v = B.var("D")  # ldl.c:319-320
+                    B.put(("regu", v, dacc[r]))
+                    B.stg(R["endd"].c, v)
+                    pending.discard(R["endd"].c)
+                    B.step()
+                    left.remove(r)
+                    finished = True
+                elif not (any(o.f1 in pending for o in R["chains"][t]) or R["divacc"][t].f1 in pending):
+                    ready.append(r)
+            if not ready:
+                assert finished, "row block cannot make progress"
+                continue
+            # the ready chains (one per row, mostly the same column of different rows), term by term: a chain
+            # keeps its own order, and chains whose next operand is the same element of L take it together
+            todo = {r: list(rows[r]["chains"][nxt[r]]) for r in ready}
+            acc = {r: None for r in ready}
+            turn = 0
+            while any(todo.values()):
+                order = [r for r in ready if todo[r]]
+                lead = order[turn % len(order)]
+                turn += 1
+                x = todo[lead][0].f1
+                for r in order:
+                    if todo[r][0].f1 != x:
+                        continue
+                    o = todo[r].pop(0)
+                    in_regs, base = where[r][0] == "regs", where[r][1]
+                    P = B.operand(o.f1)  # y_t = K(t, k) - sum L(t, i) y_i in the row's own order (ldl.c:300-304)
+                    if o.w & INIT:
+                        acc[r] = P
+                    else:
+                        yi = None if o.w & ONE else (Y[(r, o.f2)] if in_regs else B.lds(base + o.f2))
+                        v = B.var("y")
+                        B.put(("msub", v, "0.0" if o.w & FIRSTZ else acc[r], P, yi))
+                        acc[r] = v
+                    B.step()
+            for r in ready:
+                t, dv = nxt[r], rows[r]["divacc"][nxt[r]]
+                if where[r][0] == "regs":
+                    Y[(r, t)] = acc[r]
                 else:
-                    base = "0.0" if w & FIRSTZ else "t"
-                    prod = o.name if w & ONE else f"{o.name} * {s}"
-                    out.append(f"\tt = {base} - {prod};")
-            elif o.op == DIVACC:
-                out.append(f"\tt = {div}({s}, {o.name}); d = d - t * {s};")
-            elif o.op == DIV:
-                out.append(f"\tt = {div}({s}, {o.name});")
-            elif o.op == INITD:
-                out.append(f"\td = {o.name};")
-            elif o.op == ENDD:
-                out.append("\tt = regularise(d);")
-            elif o.op == LOADS:
-                out.append(f"\tt = {s};")
-            if w & ST_HBM:
-                out.append(f'\tasm volatile("st.global.f64 [%0+{o.c << 8}], %1;" :: "l"(g), "d"(t) : "memory");')
-            if w & ST_SHARED:
-                out.append(f'\tasm volatile("st.shared.f64 [%0+{o.c << 8}], %1;" :: "r"(sb), "d"(t) : "memory");')
-        out.append("\treturn make_double2(t, d);\n}\n")
-    # The warps of the CTA meet before every chunk, so that they fetch the same instructions at about the
-    # same time (the code is far larger than the instruction caches); a warp with nothing to do skips the work.
-    out.append(f"__device__ __forceinline__ void {name}(double *slice, const unsigned sb, const bool mine)\n{{")
+                    B.sts(where[r][1] + t, acc[r])
+                Dv = B.operand(dv.f1)  # l = y / D[i]; D[k] -= l*y; L(k, i) = l  (ldl.c:305-309)
+                l = B.var("l")
+                B.put(("div", l, acc[r], Dv))
+                d2 = B.var("d")
+                B.put(("msub", d2, dacc[r], l, acc[r]))
+                dacc[r] = d2
+                B.stg(dv.c, l)
+                pending.discard(dv.c)
+                B.step()
+                nxt[r] += 1
+    B.fn = None
+
+
+def build_segment(seg, ops, consts, opt, scratch):
+    B = Builder(seg, consts, opt, scratch)
+    if seg == "factor" and opt["rows"] > 0:
+        build_factor(B, ops)
+    else:
+        B.generic_run(ops)
+    return B
+
+
+def statements(fn: Function):
+    """The function's statements with each load inserted where it was scheduled."""
+    loads = sorted(fn.loads, key=lambda l: l[0])
+    out, li = [], 0
+    for pos, st in fn.items:
+        while li < len(loads) and loads[li][0] <= pos:
+            out.append(("ldg", loads[li][1], loads[li][2]))
+            li += 1
+        out.append(st)
+    for l in loads[li:]:  # operands of a trailing micro-op without statements (d = P)
+        out.append(("ldg", l[1], l[2]))
+    return out
+
+
+def pressure(fn: Function):
+    """Most doubles alive at once in the function's statement order (what the register file must hold)."""
+    sts = statements(fn)
+    last, born = {}, {}
+    for i, st in enumerate(sts):
+        k = st[0]
+        uses = {"ldg": (), "lds": (), "stg": (st[2],), "sts": (st[2],), "msub": st[2:5], "div": st[2:4], "regu": (st[2],)}[k]
+        for u in uses:
+            if u is not None and u in born:
+                last[u] = i
+        if k in ("ldg", "lds", "msub", "div", "regu"):
+            born[st[1]] = i
+    for v in (fn.t, fn.d):
+        if v in born:
+            last[v] = len(sts)
+    events = []
+    for v, b in born.items():
+        events.append((b, 1))
+        events.append((last.get(v, b) + 1, -1))
+    live = most = 0
+    for _, d in sorted(events):
+        live += d
+        most = max(most, live)
+    return most
+
+
+def regularise(d):
+    """ldl.c:319-320"""
+    sign = -1.0 if d <= 0.0 else 1.0
+    return np.float64(sign * 0.0000001) if sign * d <= 0.00000000000001 else d
+
+
+def evaluate(B: Builder, G, S):
+    """Run a segment's IR on one HBM slice G and one window S (float64 arrays), in place."""
+    f64 = np.float64
+    t = d = f64(np.nan)
+    with np.errstate(all="ignore"):
+        for fn in B.functions:
+            env = {"0.0": f64(0.0), "1.0": f64(1.0), "-1.0": f64(-1.0), "t_in": t, "d_in": d}
+            for st in statements(fn):
+                k = st[0]
+                if k == "ldg":
+                    env[st[1]] = f64(G[st[2]])
+                elif k == "lds":
+                    env[st[1]] = f64(S[st[2]])
+                elif k == "stg":
+                    G[st[1]] = env[st[2]]
+                elif k == "sts":
+                    S[st[1]] = env[st[2]]
+                elif k == "msub":
+                    env[st[1]] = env[st[2]] - (env[st[3]] if st[4] is None else env[st[3]] * env[st[4]])
+                elif k == "div":
+                    env[st[1]] = env[st[2]] / env[st[3]]
+                elif k == "regu":
+                    env[st[1]] = regularise(env[st[2]])
+                else:
+                    raise ValueError(k)
+            if fn.carried:
+                t, d = env[fn.t], env[fn.d]
+
+
+def print_cuda(B: Builder, out, div):
+    """Every function takes `mine` (does this warp have work here?) and is entered by ALL warps of the
+    CTA: they meet at a barrier every `sync` micro-ops, so that they fetch the same instructions at about
+    the same time (the code is far larger than the instruction caches), and a warp with nothing to do
+    skips the work between the barriers."""
+    sync = B.opt["sync"]
+    for fn in B.functions:
+        if fn.carried:
+            out.append(f"static __device__ __noinline__ double2 {fn.name}(char *g, const unsigned sb, const bool mine, const double t_in, const double d_in)\n{{")
+        else:
+            out.append(f"static __device__ __noinline__ void {fn.name}(char *g, const unsigned sb, const bool mine)\n{{")
+        loads = sorted(fn.loads, key=lambda l: l[0])
+        names = [l[1] for l in loads] + [st[1] for _, st in fn.items if st[0] in ("lds", "msub", "div", "regu")]
+        for i in range(0, len(names), 16):
+            out.append("\tdouble " + ", ".join(names[i:i + 16]) + ";")
+        body, li, mark = [], 0, None
+
+        def flush():
+            if body:
+                out.append("\t__syncthreads();\n\tif (mine) {")
+                out.extend(body)
+                out.append("\t}")
+                body.clear()
+
+        def emit(st):
+            k = st[0]
+            if k == "ldg":
+                body.append(f'\t\tasm volatile("ld.global.f64 %0, [%1+{st[2] << 8}];" : "=d"({st[1]}) : "l"(g) : "memory");')
+            elif k == "lds":
+                body.append(f'\t\tasm volatile("ld.shared.f64 %0, [%1+{st[2] << 8}];" : "=d"({st[1]}) : "r"(sb));')
+            elif k == "stg":
+                body.append(f'\t\tasm volatile("st.global.f64 [%0+{st[1] << 8}], %1;" :: "l"(g), "d"({st[2]}) : "memory");')
+            elif k == "sts":
+                body.append(f'\t\tasm volatile("st.shared.f64 [%0+{st[1] << 8}], %1;" :: "r"(sb), "d"({st[2]}) : "memory");')
+            elif k == "msub":
+                body.append(f"\t\t{st[1]} = {st[2]} - {st[3]}{'' if st[4] is None else ' * ' + st[4]};")
+            elif k == "div":
+                body.append(f"\t\t{st[1]} = {div}({st[2]}, {st[3]});")
+            elif k == "regu":
+                body.append(f"\t\t{st[1]} = regularise({st[2]});")
+
+        for pos, st in fn.items:
+            if mark is None or pos - mark >= sync:
+                flush()
+                mark = pos
+            while li < len(loads) and loads[li][0] <= pos:
+                emit(("ldg", loads[li][1], loads[li][2]))
+                li += 1
+            emit(st)
+        for l in loads[li:]:
+            emit(("ldg", l[1], l[2]))
+        flush()
+        if fn.carried:
+            t = fn.t if fn.t[0].isdigit() or fn.t[0] == "-" or fn.t == "t_in" else f"mine ? {fn.t} : t_in"
+            d = fn.d if fn.d[0].isdigit() or fn.d[0] == "-" or fn.d == "d_in" else f"mine ? {fn.d} : d_in"
+            out.append(f"\treturn make_double2({t}, {d});")
+        out.append("}\n")
+    out.append(f"static __device__ __forceinline__ void {B.seg}(double *slice, const unsigned sb, const bool mine)\n{{")
     out.append("\tchar *g = reinterpret_cast<char *>(slice);\n\tdouble2 td = make_double2(0.0, 0.0);")
-    for ck in range(nchunks):
-        out.append(f"\t__syncthreads();\n\tif (mine) td = {name}_{ck}(g, sb, td.x, td.y);")
-    out.append("}\n")
-    return len(ops)
+    for fn in B.functions:
+        out.append(f"\ttd = {fn.name}(g, sb, mine, td.x, td.y);" if fn.carried else f"\t{fn.name}(g, sb, mine);")
+    out.append("\t(void)td;\n}\n")
 
 
-def generate(kind: str, dist: int = 32, chunk: int = 256, div: str = "div_inline", attr: str = "__noinline__") -> str:
-    from . import dogbot, qpswift as Q
-    batch = dogbot.generate(kind, 1)
-    plan = Q.Plan(batch.pattern)
+def build_all(plan, **options):
+    """The four segments of a plan's micro-programs as IR: ({segment: Builder}, options)."""
+    opt = dict(DEFAULTS)
+    opt.update({k: v for k, v in options.items() if v is not None})
     info = plan.stream_info()
     assert info["ok"] == 1
-    zero = info["layout"]["zero"]
+    lay = info["layout"]
+    consts = {lay["zero"]: "0.0", lay["one"]: "1.0", lay["mone"]: "-1.0"}
+    return {seg: build_segment(seg, live_ops(plan.stream_words(seg), lay["zero"]), consts, opt, lay["scratch"])
+            for seg in ("factor", "solve", "resid", "resz")}, opt
+
+
+def generate(kind: str, div: str = "div_inline", **options):
+    from . import dogbot, qpswift as Q
+    plan = Q.Plan(dogbot.generate(kind, 1).pattern)
     key = plan.stream_key()
+    segs, opt = build_all(plan, **options)
     out = [f"// GENERATED by apf_quadruped_b200/codegen.py for the '{kind}' pattern (micro-program key {key:#018x}); do not edit.",
-           f"// dist {dist} micro-ops of HBM operands in flight, chunks of {chunk} micro-ops.",
+           f"// options: {opt}",
            '#include "stream.cuh"', '#include "stream_gen.cuh"', "", "namespace qpb {", f"namespace gen_{kind} {{", ""]
-    counts = {}
     for seg in ("factor", "solve", "resid", "resz"):
-        counts[seg] = emit_segment(seg, plan.stream_words(seg), zero, dist, chunk, out, div, attr)
-    out += ["struct Prog", "{", "\tstatic constexpr bool cta_sync = true;",
-            "\tstatic __device__ __forceinline__ void factor(const StreamView &, double *slice, const unsigned sb, const bool mine) { gen_%s::factor(slice, sb, mine); }" % kind,
-            "\tstatic __device__ __forceinline__ void solve(const StreamView &, double *slice, const unsigned sb, const bool mine) { gen_%s::solve(slice, sb, mine); }" % kind,
-            "\tstatic __device__ __forceinline__ void resid(const StreamView &, double *slice, const unsigned sb, const bool mine) { gen_%s::resid(slice, sb, mine); }" % kind,
-            "\tstatic __device__ __forceinline__ void resz(const StreamView &, double *slice, const unsigned sb, const bool mine) { gen_%s::resz(slice, sb, mine); }" % kind,
-            "};", "", f"}} // namespace gen_{kind}", "",
+        print_cuda(segs[seg], out, div)
+    out += ["struct Prog", "{", "\tstatic constexpr bool cta_sync = true;"]
+    for seg in ("factor", "solve", "resid", "resz"):
+        out.append(f"\tstatic __device__ __forceinline__ void {seg}(const StreamView &, double *slice, const unsigned sb, const bool mine) {{ gen_{kind}::{seg}(slice, sb, mine); }}")
+    out += ["};", "", f"}} // namespace gen_{kind}", "",
             f"QPB_REGISTER_GENERATED({kind}, {key:#018x}ull, gen_{kind}::Prog)", "", "} // namespace qpb", ""]
     plan.close()
-    return "\n".join(out), counts
+    for b in segs.values():
+        b.stats["max_live"] = max(pressure(fn) for fn in b.functions)
+    return "\n".join(out), {seg: b.stats for seg, b in segs.items()}
 
 
 def main():
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("kinds", nargs="*", default=["trot", "stance", "crawl"])
     ap.add_argument("--out", default="build/gen")
-    ap.add_argument("--dist", type=int, default=32)
-    ap.add_argument("--chunk", type=int, default=256)
     ap.add_argument("--div", default="div_inline", help="div_rn: out-of-line division; div_inline: inlined")
-    ap.add_argument("--attr", default="__noinline__")
+    for k, v in DEFAULTS.items():
+        ap.add_argument(f"--{k}", type=int, default=None, help=f"default {v}")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     for kind in a.kinds:
-        src, counts = generate(kind, a.dist, a.chunk, a.div, a.attr)
+        src, stats = generate(kind, a.div, **{k: getattr(a, k) for k in DEFAULTS})
         path = os.path.join(a.out, f"stream_gen_{kind}.cu")
         old = open(path).read() if os.path.exists(path) else None
         if old != src:  # keep the time stamp when nothing changed (make)
             with open(path, "w") as f:
                 f.write(src)
-        print(f"{path}: {counts}")
+        print(f"{path}:")
+        for seg, st in stats.items():
+            print(f"  {seg}: {st}")
 
 
 if __name__ == "__main__":

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libqpswift_b200.so")
+LIB_PATH = os.environ.get("QPB_LIB") or os.path.join(HERE, "lib", "libqpswift_b200.so")  # QPB_LIB: experiments with library variants
 
 QP_OPTIMAL, QP_KKTFAIL, QP_MAXIT, QP_FATAL = 0, 1, 2, 3
 ROW_MAJOR_ORDERING, COLUMN_MAJOR_ORDERING = 20, 30

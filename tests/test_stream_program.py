@@ -229,24 +229,3 @@ def test_library_carries_specialised_kernels_for_the_wbc_patterns(qps):
     assert mpc.stream_key() not in have  # runs on the interpreter / the latency kernel
     mpc.close()
 
-
-def test_generated_source_follows_the_program_word_for_word(qps):
-    """The generator drops padding and nothing else: one statement group per live micro-op, every
-    HBM operand requested after the last store to its element and no later than its use."""
-    from apf_quadruped_b200 import codegen
-    plan = qps.Plan(dogbot.generate("trot", 1).pattern)
-    info = plan.stream_info()
-    zero = info["layout"]["zero"]
-    for seg in ("factor", "solve", "resid", "resz"):
-        words = plan.stream_words(seg)
-        ops = codegen.live_ops(words, zero)
-        st = info["segments"][seg]
-        assert len(ops) <= st["ops"] - st["nops"] and len(ops) >= st["terms"]
-        codegen.schedule_loads(ops, 32, 256)
-        last_store = {}
-        for i, o in enumerate(ops):
-            if o.uses_p:
-                assert last_store.get(o.f1, -1) < o.load_at <= i and o.load_at >= (i // 256) * 256
-            if o.w & codegen.ST_HBM:
-                last_store[o.c] = i
-    plan.close()
