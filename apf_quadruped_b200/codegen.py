@@ -41,7 +41,7 @@ import numpy as np
 TERM, DIVACC, DIV, INITD, ENDD, LOADS, NOP = 0, 2, 3, 4, 5, 6, 8
 FIRSTZ, INIT, ST_SHARED, ST_HBM, LATE1, ONE, SLOW = (1 << (52 + i) for i in range(7))
 
-DEFAULTS = dict(dist=24, reuse=16, chunk=256, rows=3, ybudget=60, fn_ops=400, block_ops=4000, sync=1000000)
+DEFAULTS = dict(dist=24, reuse=16, chunk=256, rows=3, ybudget=60, fn_ops=400, block_ops=4000, sync=1000000, pdist=0)
 
 
 class Op:
@@ -88,6 +88,7 @@ class Function:
         self.carried = carried  # True: double2 f(g, sb, t, d) returning the accumulators; False: void f(g, sb)
         self.items = []         # (position in micro-ops, statement)
         self.loads = []         # (scheduled position, variable, element)
+        self.prefetch = []      # (position, element): prefetch.global.L2
         self.t = "t_in"
         self.d = "d_in"
         self.start = start
@@ -344,26 +345,43 @@ def build_factor(B: Builder, ops):
     B.fn = None
 
 
+def add_l2_prefetch(B: Builder):
+    """Every HBM load is announced `pdist` micro-ops ahead by a prefetch into L2 (no register, no
+    scoreboard, may sit in an earlier function): the load itself then finds its line in L2."""
+    pdist = B.opt["pdist"]
+    if pdist <= 0:
+        return
+    starts = [fn.start for fn in B.functions]
+    for fn in B.functions:
+        for at, v, e in fn.loads:
+            want = max(0, at - pdist)
+            k = max(i for i, s0 in enumerate(starts) if s0 <= want)
+            B.functions[k].prefetch.append((want, e))
+            B.stats["prefetch"] = B.stats.get("prefetch", 0) + 1
+
+
 def build_segment(seg, ops, consts, opt, scratch):
     B = Builder(seg, consts, opt, scratch)
     if seg == "factor" and opt["rows"] > 0:
         build_factor(B, ops)
     else:
         B.generic_run(ops)
+    add_l2_prefetch(B)
     return B
 
 
 def statements(fn: Function):
     """The function's statements with each load inserted where it was scheduled."""
-    loads = sorted(fn.loads, key=lambda l: l[0])
+    loads = sorted([(l[0], 1, ("ldg", l[1], l[2])) for l in fn.loads] + [(p[0], 0, ("pfl2", p[1])) for p in fn.prefetch],
+                   key=lambda l: (l[0], l[1]))
     out, li = [], 0
     for pos, st in fn.items:
         while li < len(loads) and loads[li][0] <= pos:
-            out.append(("ldg", loads[li][1], loads[li][2]))
+            out.append(loads[li][2])
             li += 1
         out.append(st)
     for l in loads[li:]:  # operands of a trailing micro-op without statements (d = P)
-        out.append(("ldg", l[1], l[2]))
+        out.append(l[2])
     return out
 
 
@@ -373,6 +391,8 @@ def pressure(fn: Function):
     last, born = {}, {}
     for i, st in enumerate(sts):
         k = st[0]
+        if k == "pfl2":
+            continue
         uses = {"ldg": (), "lds": (), "stg": (st[2],), "sts": (st[2],), "msub": st[2:5], "div": st[2:4], "regu": (st[2],)}[k]
         for u in uses:
             if u is not None and u in born:
@@ -408,7 +428,9 @@ def evaluate(B: Builder, G, S):
             env = {"0.0": f64(0.0), "1.0": f64(1.0), "-1.0": f64(-1.0), "t_in": t, "d_in": d}
             for st in statements(fn):
                 k = st[0]
-                if k == "ldg":
+                if k == "pfl2":
+                    pass
+                elif k == "ldg":
                     env[st[1]] = f64(G[st[2]])
                 elif k == "lds":
                     env[st[1]] = f64(S[st[2]])
@@ -439,8 +461,9 @@ def print_cuda(B: Builder, out, div):
             out.append(f"static __device__ __noinline__ double2 {fn.name}(char *g, const unsigned sb, const bool mine, const double t_in, const double d_in)\n{{")
         else:
             out.append(f"static __device__ __noinline__ void {fn.name}(char *g, const unsigned sb, const bool mine)\n{{")
-        loads = sorted(fn.loads, key=lambda l: l[0])
-        names = [l[1] for l in loads] + [st[1] for _, st in fn.items if st[0] in ("lds", "msub", "div", "regu")]
+        loads = sorted([(l[0], 1, ("ldg", l[1], l[2])) for l in fn.loads] + [(p[0], 0, ("pfl2", p[1])) for p in fn.prefetch],
+                       key=lambda l: (l[0], l[1]))
+        names = [l[1] for l in fn.loads] + [st[1] for _, st in fn.items if st[0] in ("lds", "msub", "div", "regu")]
         for i in range(0, len(names), 16):
             out.append("\tdouble " + ", ".join(names[i:i + 16]) + ";")
         body, li, mark = [], 0, None
@@ -454,7 +477,9 @@ def print_cuda(B: Builder, out, div):
 
         def emit(st):
             k = st[0]
-            if k == "ldg":
+            if k == "pfl2":
+                body.append(f'\t\tasm volatile("prefetch.global.L2 [%0+{st[1] << 8}];" :: "l"(g));')
+            elif k == "ldg":
                 body.append(f'\t\tasm volatile("ld.global.f64 %0, [%1+{st[2] << 8}];" : "=d"({st[1]}) : "l"(g) : "memory");')
             elif k == "lds":
                 body.append(f'\t\tasm volatile("ld.shared.f64 %0, [%1+{st[2] << 8}];" : "=d"({st[1]}) : "r"(sb));')
@@ -474,11 +499,11 @@ def print_cuda(B: Builder, out, div):
                 flush()
                 mark = pos
             while li < len(loads) and loads[li][0] <= pos:
-                emit(("ldg", loads[li][1], loads[li][2]))
+                emit(loads[li][2])
                 li += 1
             emit(st)
         for l in loads[li:]:
-            emit(("ldg", l[1], l[2]))
+            emit(l[2])
         flush()
         if fn.carried:
             t = fn.t if fn.t[0].isdigit() or fn.t[0] == "-" or fn.t == "t_in" else f"mine ? {fn.t} : t_in"
