@@ -41,7 +41,7 @@ import numpy as np
 TERM, DIVACC, DIV, INITD, ENDD, LOADS, NOP = 0, 2, 3, 4, 5, 6, 8
 FIRSTZ, INIT, ST_SHARED, ST_HBM, LATE1, ONE, SLOW = (1 << (52 + i) for i in range(7))
 
-DEFAULTS = dict(dist=24, reuse=16, chunk=256, rows=3, ybudget=60, fn_ops=400, block_ops=4000, sync=1000000, pdist=0)
+DEFAULTS = dict(dist=24, reuse=16, chunk=256, rows=3, ybudget=60, fn_ops=400, block_ops=4000, sync=1000000, pdist=0, ring=0, group=4, ahead=6)
 
 
 class Op:
@@ -87,7 +87,7 @@ class Function:
         self.name = name
         self.carried = carried  # True: double2 f(g, sb, t, d) returning the accumulators; False: void f(g, sb)
         self.items = []         # (position in micro-ops, statement)
-        self.loads = []         # (scheduled position, variable, element)
+        self.loads = []         # load records: dict(v, e, at = wanted position of the request, use = position of the first use)
         self.prefetch = []      # (position, element): prefetch.global.L2
         self.t = "t_in"
         self.d = "d_in"
@@ -117,6 +117,7 @@ class Builder:
 
     def begin(self, carried):
         self.fn = Function(f"{self.seg}_{len(self.functions)}", carried, self.pos)
+        self.fn.opt = self.opt
         self.functions.append(self.fn)
         self.cache = {}  # registers do not survive a call
         self.stats["functions"] += 1
@@ -135,7 +136,9 @@ class Builder:
             return hit[0]
         v = self.var("p")
         at = max(self.pos - self.opt["dist"], self.last_store.get(e, -1) + 1, self.fn.start)
-        self.fn.loads.append((min(at, self.pos), v, e))
+        rec = dict(v=v, e=e, at=min(at, self.pos), use=self.pos)
+        self.fn.loads.append(rec)
+        self.put(("use", rec))
         self.cache[e] = [v, self.pos]
         self.stats["hbm_loads"] += 1
         return v
@@ -353,7 +356,8 @@ def add_l2_prefetch(B: Builder):
         return
     starts = [fn.start for fn in B.functions]
     for fn in B.functions:
-        for at, v, e in fn.loads:
+        for rec in fn.loads:
+            at, e = rec["at"], rec["e"]
             want = max(0, at - pdist)
             k = max(i for i, s0 in enumerate(starts) if s0 <= want)
             B.functions[k].prefetch.append((want, e))
@@ -370,18 +374,78 @@ def build_segment(seg, ops, consts, opt, scratch):
     return B
 
 
-def statements(fn: Function):
-    """The function's statements with each load inserted where it was scheduled."""
-    loads = sorted([(l[0], 1, ("ldg", l[1], l[2])) for l in fn.loads] + [(p[0], 0, ("pfl2", p[1])) for p in fn.prefetch],
-                   key=lambda l: (l[0], l[1]))
-    out, li = [], 0
+def statements(fn: Function, opt=None):
+    """The function's final statement list: every HBM operand requested where it was scheduled.
+
+    With a ring (opt["ring"] slots of one double per lane in shared memory) an operand is requested by
+    cp.async -- ("cpa", slot, e) -- and taken out of its slot at its first use -- ("ldr", v, slot) -- after a
+    cp.async.wait_group that covers its commit group; a warp's ld.global throughput is capped (about one
+    256-byte request per 160 cycles, scripts/micro/randline3.cu), cp.async's is not.  A slot is reused
+    once its previous occupant has been taken out; an operand that cannot be requested at least `ahead`
+    micro-ops before its use (stored just before, or no free slot) is an ordinary ld.global."""
+    if getattr(fn, "final", None) is not None:
+        return fn.final
+    opt = opt or getattr(fn, "opt", None) or DEFAULTS
+    ring, per_group, ahead = opt["ring"], max(1, opt["group"]), opt["ahead"]
+    sched = [(p[0], 0, ("pfl2", p[1])) for p in fn.prefetch]  # (position, order, statement)
+    recs = sorted(fn.loads, key=lambda r: (r["at"], r["use"]))
+    import heapq
+    free = [(-1, k) for k in range(ring)]  # (position of the last use of the slot's occupant, slot)
+    heapq.heapify(free)
+    copies, last_at = [], -1
+    for r in recs:
+        r["slot"] = None
+        if ring > 0:
+            at = max(r["at"], last_at)
+            freed, slot = free[0]
+            at = max(at, freed + 1)
+            if at <= r["use"] - ahead:
+                heapq.heapreplace(free, (r["use"], slot))
+                r["slot"], r["issue"], last_at = slot, at, at
+                copies.append(r)
+                continue
+        sched.append((r["at"], 2, ("ldg", r["v"], r["e"])))
+    # commit groups: closed after `group` copies, and before a copy that would be issued after a member's use
+    groups, cur = [], []
+    for r in copies:
+        if cur and (len(cur) >= per_group or r["issue"] >= min(c["use"] for c in cur)):
+            groups.append(cur)
+            cur = []
+        cur.append(r)
+    if cur:
+        groups.append(cur)
+    commit_at = []
+    for j, grp in enumerate(groups):
+        for r in grp:
+            r["group"] = j
+            sched.append((r["issue"], 1, ("cpa", r["slot"], r["e"])))
+        commit_at.append(grp[-1]["issue"])
+        sched.append((grp[-1]["issue"], 1.5, ("commit",)))
+        assert all(c["use"] > grp[-1]["issue"] for c in grp)
+    sched.sort(key=lambda x: (x[0], x[1]))
+    out, si, waited = [], 0, -1
+    import bisect
     for pos, st in fn.items:
-        while li < len(loads) and loads[li][0] <= pos:
-            out.append(loads[li][2])
-            li += 1
-        out.append(st)
-    for l in loads[li:]:  # operands of a trailing micro-op without statements (d = P)
-        out.append(l[2])
+        while si < len(sched) and sched[si][0] <= pos:
+            out.append(sched[si][2])
+            si += 1
+        if st[0] == "use":
+            r = st[1]
+            if r["slot"] is None:
+                continue
+            j = r["group"]
+            if j > waited:
+                committed = bisect.bisect_right(commit_at, pos)  # groups committed before the statements of `pos`
+                assert committed > j
+                out.append(("waitg", committed - 1 - j))
+                waited = j
+            out.append(("ldr", r["v"], r["slot"]))
+        else:
+            out.append(st)
+    for x in sched[si:]:  # requests of a trailing micro-op without statements (d = P)
+        assert x[2][0] in ("ldg", "pfl2")
+        out.append(x[2])
+    fn.final = out
     return out
 
 
@@ -391,13 +455,13 @@ def pressure(fn: Function):
     last, born = {}, {}
     for i, st in enumerate(sts):
         k = st[0]
-        if k == "pfl2":
+        if k in ("pfl2", "cpa", "commit", "waitg"):
             continue
-        uses = {"ldg": (), "lds": (), "stg": (st[2],), "sts": (st[2],), "msub": st[2:5], "div": st[2:4], "regu": (st[2],)}[k]
+        uses = {"ldg": (), "lds": (), "ldr": (), "stg": (st[2],), "sts": (st[2],), "msub": st[2:5], "div": st[2:4], "regu": (st[2],)}[k]
         for u in uses:
             if u is not None and u in born:
                 last[u] = i
-        if k in ("ldg", "lds", "msub", "div", "regu"):
+        if k in ("ldg", "lds", "ldr", "msub", "div", "regu"):
             born[st[1]] = i
     for v in (fn.t, fn.d):
         if v in born:
@@ -426,10 +490,27 @@ def evaluate(B: Builder, G, S):
     with np.errstate(all="ignore"):
         for fn in B.functions:
             env = {"0.0": f64(0.0), "1.0": f64(1.0), "-1.0": f64(-1.0), "t_in": t, "d_in": d}
+            ringv, inflight, committed = {}, [], 0
             for st in statements(fn):
                 k = st[0]
                 if k == "pfl2":
                     pass
+                elif k == "cpa":  # lands when its group is waited for; the element must not change until then
+                    inflight.append([st[1], st[2], f64(G[st[2]]), None])
+                elif k == "commit":
+                    for c in inflight:
+                        if c[3] is None:
+                            c[3] = committed
+                    committed += 1
+                elif k == "waitg":
+                    done = committed - st[1]
+                    for c in [c for c in inflight if c[3] is not None and c[3] < done]:
+                        assert f64(G[c[1]]) == c[2] or (np.isnan(c[2]) and np.isnan(G[c[1]])), "element stored while its copy was in flight"
+                        ringv[c[0]] = c[2]
+                        inflight.remove(c)
+                elif k == "ldr":
+                    assert not any(c[0] == st[2] for c in inflight), "slot read before its copy was waited for"
+                    env[st[1]] = ringv[st[2]]
                 elif k == "ldg":
                     env[st[1]] = f64(G[st[2]])
                 elif k == "lds":
@@ -458,15 +539,13 @@ def print_cuda(B: Builder, out, div):
     sync = B.opt["sync"]
     for fn in B.functions:
         if fn.carried:
-            out.append(f"static __device__ __noinline__ double2 {fn.name}(char *g, const unsigned sb, const bool mine, const double t_in, const double d_in)\n{{")
+            out.append(f"static __device__ __noinline__ double2 {fn.name}(char *g, const unsigned sb, const unsigned rb, const bool mine, const double t_in, const double d_in)\n{{")
         else:
-            out.append(f"static __device__ __noinline__ void {fn.name}(char *g, const unsigned sb, const bool mine)\n{{")
-        loads = sorted([(l[0], 1, ("ldg", l[1], l[2])) for l in fn.loads] + [(p[0], 0, ("pfl2", p[1])) for p in fn.prefetch],
-                       key=lambda l: (l[0], l[1]))
-        names = [l[1] for l in fn.loads] + [st[1] for _, st in fn.items if st[0] in ("lds", "msub", "div", "regu")]
+            out.append(f"static __device__ __noinline__ void {fn.name}(char *g, const unsigned sb, const unsigned rb, const bool mine)\n{{")
+        names = [l["v"] for l in fn.loads] + [st[1] for _, st in fn.items if st[0] in ("lds", "msub", "div", "regu")]
         for i in range(0, len(names), 16):
             out.append("\tdouble " + ", ".join(names[i:i + 16]) + ";")
-        body, li, mark = [], 0, None
+        body = []
 
         def flush():
             if body:
@@ -479,6 +558,14 @@ def print_cuda(B: Builder, out, div):
             k = st[0]
             if k == "pfl2":
                 body.append(f'\t\tasm volatile("prefetch.global.L2 [%0+{st[1] << 8}];" :: "l"(g));')
+            elif k == "cpa":
+                body.append(f'\t\tasm volatile("cp.async.ca.shared.global [%0+{st[1] << 8}], [%1+{st[2] << 8}], 8;" :: "r"(rb), "l"(g) : "memory");')
+            elif k == "commit":
+                body.append('\t\tasm volatile("cp.async.commit_group;" ::: "memory");')
+            elif k == "waitg":
+                body.append(f'\t\tasm volatile("cp.async.wait_group {st[1]};" ::: "memory");')
+            elif k == "ldr":
+                body.append(f'\t\tasm volatile("ld.shared.f64 %0, [%1+{st[2] << 8}];" : "=d"({st[1]}) : "r"(rb) : "memory");')
             elif k == "ldg":
                 body.append(f'\t\tasm volatile("ld.global.f64 %0, [%1+{st[2] << 8}];" : "=d"({st[1]}) : "l"(g) : "memory");')
             elif k == "lds":
@@ -494,26 +581,18 @@ def print_cuda(B: Builder, out, div):
             elif k == "regu":
                 body.append(f"\t\t{st[1]} = regularise({st[2]});")
 
-        for pos, st in fn.items:
-            if mark is None or pos - mark >= sync:
-                flush()
-                mark = pos
-            while li < len(loads) and loads[li][0] <= pos:
-                emit(loads[li][2])
-                li += 1
+        for st in statements(fn):
             emit(st)
-        for l in loads[li:]:
-            emit(l[2])
         flush()
         if fn.carried:
             t = fn.t if fn.t[0].isdigit() or fn.t[0] == "-" or fn.t == "t_in" else f"mine ? {fn.t} : t_in"
             d = fn.d if fn.d[0].isdigit() or fn.d[0] == "-" or fn.d == "d_in" else f"mine ? {fn.d} : d_in"
             out.append(f"\treturn make_double2({t}, {d});")
         out.append("}\n")
-    out.append(f"static __device__ __forceinline__ void {B.seg}(double *slice, const unsigned sb, const bool mine)\n{{")
+    out.append(f"static __device__ __forceinline__ void {B.seg}(double *slice, const unsigned sb, const unsigned rb, const bool mine)\n{{")
     out.append("\tchar *g = reinterpret_cast<char *>(slice);\n\tdouble2 td = make_double2(0.0, 0.0);")
     for fn in B.functions:
-        out.append(f"\ttd = {fn.name}(g, sb, mine, td.x, td.y);" if fn.carried else f"\t{fn.name}(g, sb, mine);")
+        out.append(f"\ttd = {fn.name}(g, sb, rb, mine, td.x, td.y);" if fn.carried else f"\t{fn.name}(g, sb, rb, mine);")
     out.append("\t(void)td;\n}\n")
 
 
@@ -539,14 +618,16 @@ def generate(kind: str, div: str = "div_inline", **options):
            '#include "stream.cuh"', '#include "stream_gen.cuh"', "", "namespace qpb {", f"namespace gen_{kind} {{", ""]
     for seg in ("factor", "solve", "resid", "resz"):
         print_cuda(segs[seg], out, div)
-    out += ["struct Prog", "{", "\tstatic constexpr bool cta_sync = true;"]
+    out += ["struct Prog", "{", "\tstatic constexpr bool cta_sync = true;", f"\tstatic constexpr int ring_slots = {opt['ring']};"]
     for seg in ("factor", "solve", "resid", "resz"):
-        out.append(f"\tstatic __device__ __forceinline__ void {seg}(const StreamView &, double *slice, const unsigned sb, const bool mine) {{ gen_{kind}::{seg}(slice, sb, mine); }}")
+        out.append(f"\tstatic __device__ __forceinline__ void {seg}(const StreamView &, double *slice, const unsigned sb, const unsigned rb, const bool mine) {{ gen_{kind}::{seg}(slice, sb, rb, mine); }}")
     out += ["};", "", f"}} // namespace gen_{kind}", "",
             f"QPB_REGISTER_GENERATED({kind}, {key:#018x}ull, gen_{kind}::Prog)", "", "} // namespace qpb", ""]
     plan.close()
     for b in segs.values():
         b.stats["max_live"] = max(pressure(fn) for fn in b.functions)
+        kinds = [st[0] for fn in b.functions for st in statements(fn)]
+        b.stats.update(ring_loads=kinds.count("cpa"), direct_loads=kinds.count("ldg"), waits=kinds.count("waitg"))
     return "\n".join(out), {seg: b.stats for seg, b in segs.items()}
 
 

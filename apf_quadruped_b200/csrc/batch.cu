@@ -36,9 +36,9 @@ static std::vector<GeneratedKernel> &generated_kernels()
 	static std::vector<GeneratedKernel> v;
 	return v;
 }
-void register_generated_kernel(unsigned long long key, const void *kernel, const char *name)
+void register_generated_kernel(unsigned long long key, const void *kernel, const char *name, int ring_slots)
 {
-	generated_kernels().push_back(GeneratedKernel{key, kernel, name});
+	generated_kernels().push_back(GeneratedKernel{key, kernel, name, ring_slots});
 }
 const GeneratedKernel *find_generated_kernel(unsigned long long key)
 {
@@ -284,6 +284,9 @@ struct QPBatch
 	int *d_flag = nullptr, *d_iters = nullptr;
 	int *h_flag = nullptr, *h_iters = nullptr; // pinned
 	cudaStream_t stream = nullptr;
+	cudaStream_t copy_stream = nullptr; // QP_SOLVE_BATCH: the value rows travel while the throughput kernel runs
+	cudaEvent_t ev_go = nullptr;
+	int *h_marks = nullptr;             // pinned: the "rows [0, mark) have arrived" values written after each chunk
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	double last_kernel_ms = 0.0;
 	long last_launches = 0;
@@ -321,7 +324,9 @@ static int batch_alloc(QPBatch *B)
 	CUDA_TRY(cudaMalloc(&B->d_counter, 64 * sizeof(int)));
 	// ---- throughput kernel: one thread per QP, slices interleaved in an HBM workspace ---------------
 	if (B->sprog.ok) {
-		const size_t window = (size_t)B->sprog.lay.scratch * 32 * sizeof(double); // shared memory per warp: the lanes' work vectors
+		if (!getenv("QPB_STREAM_INTERPRET")) B->generated = find_generated_kernel(stream_program_key(B->sprog));
+		// shared memory per warp: the lanes' work vectors, plus the operand ring of a generated program
+		const size_t window = (size_t)(B->sprog.lay.scratch + (B->generated ? B->generated->ring_slots : 0)) * 32 * sizeof(double);
 		long cap = getenv("QPB_STREAM_WARPS") ? atol(getenv("QPB_STREAM_WARPS")) : STREAM_MAX_WARPS;
 		if (cap > STREAM_MAX_WARPS) cap = STREAM_MAX_WARPS;
 		B->stream_warps = (int)std::min<size_t>((size_t)std::max(cap, 1L), B->smem_limit / window);
@@ -333,7 +338,6 @@ static int batch_alloc(QPBatch *B)
 		CUDA_TRY(cudaMalloc(&B->d_stream, sp.words.size() * sizeof(uint64_t)));
 		CUDA_TRY(cudaMemcpy(B->d_stream, sp.words.data(), sp.words.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
 		B->sview.words = B->d_stream;
-		if (!getenv("QPB_STREAM_INTERPRET")) B->generated = find_generated_kernel(stream_program_key(sp));
 		if (B->generated) CUDA_TRY(cudaFuncSetAttribute(B->generated->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
 		for (int s = 0; s < SSEG_COUNT; ++s) { B->sview.first[s] = sp.seg[s].first; B->sview.groups[s] = sp.seg[s].groups; }
 		const long full = (long)B->sm_count * B->stream_warps;
@@ -347,6 +351,9 @@ static int batch_alloc(QPBatch *B)
 		if (B->capacity >= B->stream_min) CUDA_TRY(cudaMalloc(&B->d_workspace, (size_t)B->stream_slots * sp.lay.total * 32 * sizeof(double)));
 	}
 	CUDA_TRY(cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking));
+	CUDA_TRY(cudaStreamCreateWithFlags(&B->copy_stream, cudaStreamNonBlocking));
+	CUDA_TRY(cudaEventCreateWithFlags(&B->ev_go, cudaEventDisableTiming));
+	CUDA_TRY(cudaMallocHost(&B->h_marks, 256 * sizeof(int)));
 	CUDA_TRY(cudaEventCreate(&B->ev0));
 	CUDA_TRY(cudaEventCreate(&B->ev1));
 	return 0;
@@ -399,7 +406,7 @@ static int launch_stream(QPBatch *B, BatchIO io, SolveParams prm, cudaStream_t s
 	long slots = std::min(B->stream_slots, ((long)io.count + 31) / 32);
 	const long warps = std::min<long>(B->stream_warps, std::max(1L, (slots + B->sm_count - 1) / B->sm_count));
 	const long grid = (slots + warps - 1) / warps;
-	const size_t smem = (size_t)warps * sp.lay.scratch * 32 * sizeof(double);
+	const size_t smem = (size_t)warps * (sp.lay.scratch + (B->generated ? B->generated->ring_slots : 0)) * 32 * sizeof(double);
 	StreamDims dm;
 	dm.n = (int)B->plan.n; dm.m = (int)B->plan.m; dm.p = (int)B->plan.p; dm.N = (int)B->plan.N;
 	dm.nnzP = (int)B->plan.nnzP; dm.nnzA = (int)B->plan.nnzA; dm.nnzG = (int)B->plan.nnzG;
@@ -449,6 +456,7 @@ static int launch_fused(QPBatch *B, BatchIO io, const settings *opts, cudaStream
 	io.count_ptr = nullptr;
 	io.spill = nullptr;
 	io.spill_count = nullptr;
+	if (!(B->d_workspace && io.count >= B->stream_min)) io.ready = nullptr; // only the throughput kernel waits for rows
 	CUDA_TRY(cudaMemsetAsync(B->d_counter, 0, sizeof(int), st));
 	if (B->d_workspace && io.count >= B->stream_min) return launch_stream(B, io, prm, st);
 	B->last_kernel = 0;
@@ -508,6 +516,9 @@ void QP_CLEANUP_BATCH(QPBatch *B)
 	if (B->h_flag) cudaFreeHost(B->h_flag);
 	if (B->h_iters) cudaFreeHost(B->h_iters);
 	if (B->stream) cudaStreamDestroy(B->stream);
+	if (B->copy_stream) cudaStreamDestroy(B->copy_stream);
+	if (B->ev_go) cudaEventDestroy(B->ev_go);
+	if (B->h_marks) cudaFreeHost(B->h_marks);
 	if (B->ev0) cudaEventDestroy(B->ev0);
 	if (B->ev1) cudaEventDestroy(B->ev1);
 	cudaGetLastError();
@@ -523,6 +534,7 @@ qp_int QP_SOLVE_BATCH_DEVICE(QPBatch *B, qp_int count, const settings *opts, con
 	io.Ppr = dPpr; io.Apr = dApr; io.Gpr = dGpr; io.c = dc; io.h = dh; io.b = db;
 	io.x = dx; io.y = dy; io.z = dz; io.s = ds; io.flag = dflag; io.iters = diters; io.fval = dfval; io.stat = dstat;
 	io.count = (int)count;
+	io.ready = nullptr;
 	return launch_fused(B, io, opts, (cudaStream_t)stream);
 }
 
@@ -539,15 +551,42 @@ qp_int QP_SOLVE_BATCH(QPBatch *B, qp_int count, const settings *opts, const qp_r
 	const size_t n = (size_t)count;
 	const qp_real *src[6] = {Ppr, Apr, Gpr, c, h, b};
 	const size_t widths[6] = {(size_t)pl.nnzP, (size_t)pl.nnzA, (size_t)pl.nnzG, (size_t)pl.n, (size_t)pl.m, (size_t)pl.p};
-	for (int i = 0; i < 6; ++i)
-		if (widths[i]) CUDA_TRY(cudaMemcpyAsync(B->d_in[i], src[i], n * widths[i] * sizeof(double), cudaMemcpyHostToDevice, st));
 	BatchIO io;
 	io.Ppr = B->d_in[0]; io.Apr = B->d_in[1]; io.Gpr = B->d_in[2]; io.c = B->d_in[3]; io.h = B->d_in[4]; io.b = B->d_in[5];
 	io.x = B->d_x; io.y = B->d_y; io.z = B->d_z; io.s = B->d_s; io.flag = B->d_flag; io.iters = B->d_iters; io.fval = B->d_fval; io.stat = B->d_stat;
 	io.count = (int)count;
-	CUDA_TRY(cudaEventRecord(B->ev0, st));
-	rc = launch_fused(B, io, opts, st);
-	if (rc) return rc;
+	io.ready = nullptr;
+	const bool overlap = B->d_workspace && count >= B->stream_min && !getenv("QPB_NO_OVERLAP");
+	if (!overlap) {
+		for (int i = 0; i < 6; ++i)
+			if (widths[i]) CUDA_TRY(cudaMemcpyAsync(B->d_in[i], src[i], n * widths[i] * sizeof(double), cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaEventRecord(B->ev0, st));
+		rc = launch_fused(B, io, opts, st);
+		if (rc) return rc;
+	} else {
+		// The throughput kernel takes QPs in index order from a queue, so it can start on the first rows while
+		// the rest is still on its way: the rows go up in chunks on a second stream, each followed by the mark
+		// "rows [0, m) have arrived" (d_counter[40]); a warp that has taken QPs beyond the mark waits for it.
+		int *ready = B->d_counter + 40;
+		io.ready = ready;
+		CUDA_TRY(cudaMemsetAsync(ready, 0, sizeof(int), st));
+		CUDA_TRY(cudaEventRecord(B->ev_go, st));
+		CUDA_TRY(cudaStreamWaitEvent(B->copy_stream, B->ev_go, 0));
+		// (the copies are queued BEFORE the launch: a tool that makes launches synchronous must not wait for
+		// a kernel whose input is not even on its way)
+		const size_t chunk = std::max<size_t>(2048, (n + 63) / 64);
+		int k = 0;
+		for (size_t lo = 0; lo < n; lo += chunk, ++k) {
+			const size_t cnt = std::min(chunk, n - lo);
+			for (int i = 0; i < 6; ++i)
+				if (widths[i]) CUDA_TRY(cudaMemcpyAsync(B->d_in[i] + lo * widths[i], src[i] + lo * widths[i], cnt * widths[i] * sizeof(double), cudaMemcpyHostToDevice, B->copy_stream));
+			B->h_marks[k] = (int)(lo + cnt);
+			CUDA_TRY(cudaMemcpyAsync(ready, B->h_marks + k, sizeof(int), cudaMemcpyHostToDevice, B->copy_stream));
+		}
+		CUDA_TRY(cudaEventRecord(B->ev0, st));
+		rc = launch_fused(B, io, opts, st);
+		if (rc) return rc;
+	}
 	CUDA_TRY(cudaEventRecord(B->ev1, st));
 	if (x) CUDA_TRY(cudaMemcpyAsync(x, B->d_x, n * pl.n * sizeof(double), cudaMemcpyDeviceToHost, st));
 	if (y && pl.p) CUDA_TRY(cudaMemcpyAsync(y, B->d_y, n * pl.p * sizeof(double), cudaMemcpyDeviceToHost, st));

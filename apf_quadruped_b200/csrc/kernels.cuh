@@ -47,6 +47,9 @@ struct BatchIO
 	const int *index;     // null: QP i is QP i
 	const int *count_ptr; // null: count
 	int *spill, *spill_count; // throughput kernel: where it lists the QPs it hands over (null: it never does)
+	// throughput kernel behind QP_SOLVE_BATCH: the value rows are still arriving from the host while the kernel
+	// runs; QPs [0, *ready) are there (null: all of them are)
+	const int *ready;
 };
 
 #ifdef __CUDACC__

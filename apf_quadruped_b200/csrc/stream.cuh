@@ -241,10 +241,11 @@ template <int G>
 struct InterpretedProgram
 {
 	static constexpr bool cta_sync = false; // the warps of a CTA never wait for one another
-	static __device__ __forceinline__ void factor(const StreamView &sv, double *slice, const unsigned sb, bool) { run_stream<G, false, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_FACTOR], sv.groups[SSEG_FACTOR], slice, sb); }
-	static __device__ __forceinline__ void solve(const StreamView &sv, double *slice, const unsigned sb, bool) { run_stream<G, false, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], slice, sb); }
-	static __device__ __forceinline__ void resid(const StreamView &sv, double *slice, const unsigned sb, bool) { run_stream<G, true, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_RESID], sv.groups[SSEG_RESID], slice, sb); }
-	static __device__ __forceinline__ void resz(const StreamView &sv, double *slice, const unsigned sb, bool) { run_stream<G, true, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_RESZ], sv.groups[SSEG_RESZ], slice, sb); }
+	static constexpr int ring_slots = 0;    // no operand ring in shared memory (see stream_gen.cuh)
+	static __device__ __forceinline__ void factor(const StreamView &sv, double *slice, const unsigned sb, unsigned, bool) { run_stream<G, false, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_FACTOR], sv.groups[SSEG_FACTOR], slice, sb); }
+	static __device__ __forceinline__ void solve(const StreamView &sv, double *slice, const unsigned sb, unsigned, bool) { run_stream<G, false, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_SOLVE], sv.groups[SSEG_SOLVE], slice, sb); }
+	static __device__ __forceinline__ void resid(const StreamView &sv, double *slice, const unsigned sb, unsigned, bool) { run_stream<G, true, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_RESID], sv.groups[SSEG_RESID], slice, sb); }
+	static __device__ __forceinline__ void resz(const StreamView &sv, double *slice, const unsigned sb, unsigned, bool) { run_stream<G, true, STREAM_FS_DEPTH(G)>(sv.words + sv.first[SSEG_RESZ], sv.groups[SSEG_RESZ], slice, sb); }
 };
 
 // Does any lane want this step?  A program with cta_sync = true (generated straight-line code, which
@@ -270,6 +271,8 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 	double *tile = workspace + (size_t)slot * L.total * 32; // the warp's 32 interleaved slices
 	double *g = tile + lane;
 	const unsigned sb = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)(warp * L.scratch * 32 + lane) * 8u;
+	// behind the windows of all warps: this warp's ring of HBM operands on their way in (generated programs only)
+	const unsigned rb = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)((blockDim.x >> 5) * L.scratch * 32 + warp * PROG::ring_slots * 32 + lane) * 8u;
 	const int n = dm.n, m = dm.m, p = dm.p, np = dm.n + dm.p, N = dm.N;
 	const double thr = prm.reltol / sqrt(3.0);
 	if (live) {
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 				STREAM_FOR(n, a8[j] = SL(L.x + i);, sts64(sb + ((unsigned)i << 8), a8[j]);)
 				STREAM_FOR(p, a8[j] = SL(L.y + i);, sts64(sb + ((unsigned)(n + i) << 8), a8[j]);)
 			}
-			PROG::resid(sv, g, sb, mine);
+			PROG::resid(sv, g, sb, rb, mine);
 			if (need_res) {
 				sc.n_rx = sqrt(stream_dot(g + (L.r << 5), g + (L.r << 5), n));
 				if (p) sc.n_ry = sqrt(stream_dot(g + ((L.r + n) << 5), g + ((L.r + n) << 5), p));
@@ -351,6 +354,11 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 				if (q < io.count) fresh = true;
 				else { exhausted = true; q = -1; }
 			}
+			if (io.ready) { // host-pointer entry: wait until the rows of the QPs just taken have arrived (batch.cu)
+				const int last = __reduce_max_sync(FULL, fresh ? q : -1);
+				while (*reinterpret_cast<const volatile int *>(io.ready) <= last) __nanosleep(500);
+				__threadfence(); // the rows were written by a copy engine before the mark
+			}
 			unsigned got = __ballot_sync(FULL, fresh);
 			while (got) { // the warp transposes one value row at a time into the owner's slice
 				const int dst = __ffs(got) - 1;
@@ -358,13 +366,13 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 				const size_t qi = (size_t)__shfl_sync(FULL, q, dst);
 				double *to = tile + dst;
 				// "+ 0.0": the reference's Y[i] += value from Y[i] == 0 (ldl.c:284), see stream_program.h
-				for (int e = lane; e < dm.nnzP; e += 32) to[(L.V + e) << 5] = __ldg(io.Ppr + qi * dm.nnzP + e) + 0.0;
-				for (int e = lane; e < dm.nnzA; e += 32) to[(L.V + dm.nnzP + e) << 5] = __ldg(io.Apr + qi * dm.nnzA + e) + 0.0;
-				for (int e = lane; e < dm.nnzG; e += 32) to[(L.V + dm.nnzP + dm.nnzA + e) << 5] = __ldg(io.Gpr + qi * dm.nnzG + e) + 0.0;
-				for (int e = lane; e < n; e += 32) to[(L.c + e) << 5] = __ldg(io.c + qi * n + e);
-				for (int e = lane; e < m; e += 32) to[(L.h + e) << 5] = __ldg(io.h + qi * m + e);
+				for (int e = lane; e < dm.nnzP; e += 32) to[(L.V + e) << 5] = io.Ppr[qi * dm.nnzP + e] + 0.0;
+				for (int e = lane; e < dm.nnzA; e += 32) to[(L.V + dm.nnzP + e) << 5] = io.Apr[qi * dm.nnzA + e] + 0.0;
+				for (int e = lane; e < dm.nnzG; e += 32) to[(L.V + dm.nnzP + dm.nnzA + e) << 5] = io.Gpr[qi * dm.nnzG + e] + 0.0;
+				for (int e = lane; e < n; e += 32) to[(L.c + e) << 5] = io.c[qi * n + e];
+				for (int e = lane; e < m; e += 32) to[(L.h + e) << 5] = io.h[qi * m + e];
 				for (int e = lane; e < p; e += 32) {
-					const double be = __ldg(io.b + qi * p + e);
+					const double be = io.b[qi * p + e];
 					to[(L.b + e) << 5] = be;
 					to[(L.nb + e) << 5] = -be;
 				}
@@ -399,8 +407,8 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 		if (!any_wants<PROG>(mode != SM_IDLE)) break;
 		const bool busy = __any_sync(FULL, mode != SM_IDLE);
 
-		PROG::factor(sv, g, sb, busy);
-		PROG::solve(sv, g, sb, busy);
+		PROG::factor(sv, g, sb, rb, busy);
+		PROG::solve(sv, g, sb, rb, busy);
 
 		// ---- kkt_initialize, second half (Auxilary.c:1044-1083) ------------------------------------------
 		if (any_wants<PROG>(mode == SM_INIT)) {
@@ -410,7 +418,7 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 				STREAM_FOR(p, a8[j] = SL(L.rhs + n + i);, SL(L.y + i) = a8[j];)
 				STREAM_FOR(m, a8[j] = SL(L.h + i);, SL(L.hs + i) = -a8[j];)
 			}
-			PROG::resz(sv, g, sb, mine); // hs <- -(G x) - (-h) = h - G x
+			PROG::resz(sv, g, sb, rb, mine); // hs <- -(G x) - (-h) = h - G x
 			if (mode == SM_INIT) {
 				const double inf = __longlong_as_double(0x7ff0000000000000LL);
 				double lo = inf, hi = -inf;
@@ -459,7 +467,7 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 			STREAM_FOR(np, a8[j] = SL(L.r + i);, SL(L.rhs + i) = a8[j];)
 		}
 		if (any_wants<PROG>(mode == SM_PRED)) {
-			PROG::solve(sv, g, sb, __any_sync(FULL, mode == SM_PRED));
+			PROG::solve(sv, g, sb, rb, __any_sync(FULL, mode == SM_PRED));
 			if (mode == SM_PRED) step(true);
 		}
 		(void)N;
