@@ -226,32 +226,30 @@ __device__ __forceinline__ void load_words(uint2 (&dst)[U], const uint2 *__restr
 	}
 }
 
-// Runs `waves` super-waves (a multiple of PROGRAM_WAVE_PAD == 3) starting `first` * 32 words into
-// `prog`.  Three super-waves' worth of instruction words are always in flight (read-only path, L1
-// resident while the warps of a CTA run the same segment); the program buffer is padded so the
-// prefetch needs no bounds check.
+// Runs `waves` super-waves (a multiple of PROGRAM_WAVE_PAD) starting `first` * 32 words into `prog`.
+// PROGRAM_WAVE_PAD super-waves' worth of instruction words are always in flight (read-only path): a warp
+// that runs alone on its SM -- the stragglers of the throughput kernel, the single-QP QP_SOLVE -- gets
+// every word from L2, and a super-wave is much shorter than that round trip; the program buffer is padded
+// so the prefetch needs no bounds check.
 template <int U>
 __device__ __forceinline__ void run_segment_w(const uint2 *__restrict__ prog, int first, int waves, const unsigned sb)
 {
+	constexpr int D = PROGRAM_WAVE_PAD;
 	const uint2 *p = prog + (size_t)first * 32 + lane_id() * U;
-	uint2 A[U], B[U], C[U];
-	load_words<U>(A, p);
-	load_words<U>(B, p + 32 * U);
-	load_words<U>(C, p + 64 * U);
+	uint2 W[D][U];
+#pragma unroll
+	for (int k = 0; k < D; ++k) load_words<U>(W[k], p + 32 * U * k);
 	double t[U];
 #pragma unroll
 	for (int u = 0; u < U; ++u) t[u] = 0.0;
-	for (int w = 0; w < waves; w += 3) {
-		p += 96 * U;
-		exec_super<U>(A, t, sb);
-		__syncwarp();
-		load_words<U>(A, p);
-		exec_super<U>(B, t, sb);
-		__syncwarp();
-		load_words<U>(B, p + 32 * U);
-		exec_super<U>(C, t, sb);
-		__syncwarp();
-		load_words<U>(C, p + 64 * U);
+	for (int w = 0; w < waves; w += D) {
+		p += 32 * U * D;
+#pragma unroll
+		for (int k = 0; k < D; ++k) {
+			exec_super<U>(W[k], t, sb);
+			__syncwarp();
+			load_words<U>(W[k], p + 32 * U * k);
+		}
 	}
 }
 

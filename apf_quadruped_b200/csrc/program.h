@@ -65,7 +65,7 @@ enum : uint64_t
 	INS_SUMWAVE = 1ull << 62, INS_DIVWAVE = 1ull << 63
 };
 static const int INS_ADDR_BITS = 14;
-static const int PROGRAM_WAVE_PAD = 3; // segments are padded to a multiple of this many super-waves (kernel prefetch depth)
+static const int PROGRAM_WAVE_PAD = 6; // segments are padded to a multiple of this many super-waves (kernel prefetch depth)
 
 struct SegmentStats
 {
