@@ -208,6 +208,34 @@ static __device__ __noinline__ double stream_dot(const double *a, const double *
 	return acc;
 }
 
+// One row of the API's row-per-QP arrays into a lane's slice (element e at to[e << 5]); the warp reads 256
+// bytes at a time, eight such requests in flight.  PLUS_ZERO: v + 0.0 (-0.0 becomes +0.0).
+template <bool PLUS_ZERO>
+__device__ __forceinline__ void stream_take_row(double *to, const double *row, const int count, const int lane)
+{
+	for (int e0 = lane; e0 < count; e0 += 8 * 32) {
+		double v[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) v[j] = row[min(e0 + 32 * j, count - 1)];
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			if (e0 + 32 * j < count) to[(size_t)(e0 + 32 * j) << 5] = PLUS_ZERO ? v[j] + 0.0 : v[j];
+	}
+}
+
+// ... and a vector of a lane's slice out into a row of the API's arrays (up to 128 elements in flight).
+__device__ __forceinline__ void stream_give_row(double *row, const double *from, const int count, const int lane)
+{
+	for (int e0 = lane; e0 < count; e0 += 4 * 32) {
+		double v[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) v[j] = from[(size_t)min(e0 + 32 * j, count - 1) << 5];
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			if (e0 + 32 * j < count) row[e0 + 32 * j] = v[j];
+	}
+}
+
 // Out of line on purpose: an inlined FP64 division / square root is ~30 instructions, and the elementwise
 // steps below are unrolled eight-fold; the kernel has to stay friendly to the instruction cache.
 static __device__ __noinline__ double div_rn(const double a, const double b) { return a / b; }
@@ -366,11 +394,11 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 				const size_t qi = (size_t)__shfl_sync(FULL, q, dst);
 				double *to = tile + dst;
 				// "+ 0.0": the reference's Y[i] += value from Y[i] == 0 (ldl.c:284), see stream_program.h
-				for (int e = lane; e < dm.nnzP; e += 32) to[(L.V + e) << 5] = io.Ppr[qi * dm.nnzP + e] + 0.0;
-				for (int e = lane; e < dm.nnzA; e += 32) to[(L.V + dm.nnzP + e) << 5] = io.Apr[qi * dm.nnzA + e] + 0.0;
-				for (int e = lane; e < dm.nnzG; e += 32) to[(L.V + dm.nnzP + dm.nnzA + e) << 5] = io.Gpr[qi * dm.nnzG + e] + 0.0;
-				for (int e = lane; e < n; e += 32) to[(L.c + e) << 5] = io.c[qi * n + e];
-				for (int e = lane; e < m; e += 32) to[(L.h + e) << 5] = io.h[qi * m + e];
+				stream_take_row<true>(to + ((size_t)L.V << 5), io.Ppr + qi * dm.nnzP, dm.nnzP, lane);
+				stream_take_row<true>(to + ((size_t)(L.V + dm.nnzP) << 5), io.Apr + qi * dm.nnzA, dm.nnzA, lane);
+				stream_take_row<true>(to + ((size_t)(L.V + dm.nnzP + dm.nnzA) << 5), io.Gpr + qi * dm.nnzG, dm.nnzG, lane);
+				stream_take_row<false>(to + ((size_t)L.c << 5), io.c + qi * n, n, lane);
+				stream_take_row<false>(to + ((size_t)L.h << 5), io.h + qi * m, m, lane);
 				for (int e = lane; e < p; e += 32) {
 					const double be = io.b[qi * p + e];
 					to[(L.b + e) << 5] = be;
