@@ -284,6 +284,11 @@ struct QPBatch
 	int *d_flag = nullptr, *d_iters = nullptr;
 	int *h_flag = nullptr, *h_iters = nullptr; // pinned
 	cudaStream_t stream = nullptr;
+	// dense front-end (QPB_DENSE_TO_VALUES_DEVICE): position of every dense entry in the value row, or -1
+	int *d_dense_map[3] = {nullptr, nullptr, nullptr};
+	int dense_map_ordering = 0;
+	double *d_dense[3] = {nullptr, nullptr, nullptr}; // staging of the host-pointer entry
+	int *d_violation = nullptr;
 	cudaStream_t copy_stream = nullptr; // QP_SOLVE_BATCH: the value rows travel while the throughput kernel runs
 	cudaEvent_t ev_go = nullptr;
 	int *h_marks = nullptr;             // pinned: the "rows [0, mark) have arrived" values written after each chunk
@@ -464,6 +469,78 @@ static int launch_fused(QPBatch *B, BatchIO io, const settings *opts, cudaStream
 	return launch_latency(B, io, prm, io.count, B->d_counter, st);
 }
 
+static qp_int qp_solve_batch_host(QPBatch *B, qp_int count, const settings *opts, const qp_real *Ppr, const qp_real *Apr, const qp_real *Gpr, const qp_real *c, const qp_real *h, const qp_real *b, qp_real *x, qp_real *y, qp_real *z, qp_real *s, qp_int *flag, qp_int *iters);
+
+// ---- dense front-end ----------------------------------------------------------------
+// densetosparse / densetosparse_ROWMAJOR (Auxilary.c:1154-1273) for a whole batch against ONE fixed
+// pattern: the value of every entry of the plan's pattern goes to its place in the value row; what
+// the reference's data-dependent pattern would have done differently is reported per QP
+// (bit 0: a nonzero outside the pattern, bit 1: an exact zero inside it).  The dense blocks are read
+// front to back (coalesced), the 4-byte map entries stay in L1/L2, a row's values land next to each other.
+// Every thread walks the cells of ALL QPs of one matrix with a grid stride (no idle lanes at the end of a
+// 900- or 360-cell block), four requests in flight; the violation bits are rare and go out by atomicOr.
+__device__ __forceinline__ void dense_gather_all(const double *__restrict__ dense, const int *__restrict__ map, const unsigned cells, const unsigned nnz, double *__restrict__ rows, int *__restrict__ violation, const unsigned first_qp, const unsigned total)
+{
+	// (32-bit cell numbers: the host splits a batch whose matrix has 2^32 cells or more into several launches)
+	const unsigned stride = gridDim.x * blockDim.x;
+	dense += (size_t)first_qp * cells;
+	for (unsigned g0 = blockIdx.x * blockDim.x + threadIdx.x; g0 < total; g0 += 4 * stride) {
+		double v[4];
+		int k[4];
+		unsigned q[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const unsigned g = min(g0 + j * stride, total - 1);
+			q[j] = g / cells;
+			v[j] = dense[g];
+			k[j] = __ldg(map + (g - q[j] * cells));
+		}
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			if (g0 + j * stride >= total || g0 + j * stride < g0) continue;
+			int bits = 0;
+			if (k[j] >= 0) {
+				rows[(size_t)(first_qp + q[j]) * nnz + k[j]] = v[j];
+				if (v[j] == 0.0) bits = 2;
+			} else if (v[j] != 0.0) bits = 1;
+			if (bits && violation) atomicOr(violation + first_qp + q[j], bits);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) dense_gather_kernel(const double *__restrict__ dP, const double *__restrict__ dA, const double *__restrict__ dG, const int *__restrict__ mapP, const int *__restrict__ mapA, const int *__restrict__ mapG, const int n, const int m, const int p, const int nnzP, const int nnzA, const int nnzG, double *__restrict__ oP, double *__restrict__ oA, double *__restrict__ oG, int *__restrict__ violation, const int first_qp, const int count)
+{
+	dense_gather_all(dG, mapG, (unsigned)(m * n), (unsigned)nnzG, oG, violation, (unsigned)first_qp, (unsigned)count * (unsigned)(m * n));
+	dense_gather_all(dP, mapP, (unsigned)(n * n), (unsigned)nnzP, oP, violation, (unsigned)first_qp, (unsigned)count * (unsigned)(n * n));
+	if (p) dense_gather_all(dA, mapA, (unsigned)(p * n), (unsigned)nnzA, oA, violation, (unsigned)first_qp, (unsigned)count * (unsigned)(p * n));
+}
+
+static int ensure_dense_maps(QPBatch *B, int ordering)
+{
+	if (B->d_dense_map[0] && B->dense_map_ordering == ordering) return 0;
+	const Plan &pl = B->plan;
+	const DevicePlanHeader *hd = reinterpret_cast<const DevicePlanHeader *>(pl.blob.data());
+	const int32_t *blob = pl.blob.data();
+	const long n = pl.n;
+	struct View { long rows; int32_t ptr, col, val; long off; };
+	const View views[3] = {{pl.n, hd->prow_ptr, hd->prow_col, hd->prow_val, 0}, {pl.p, hd->arow_ptr, hd->arow_col, hd->arow_val, pl.nnzP}, {pl.m, hd->grow_ptr, hd->grow_col, hd->grow_val, pl.nnzP + pl.nnzA}};
+	for (int k = 0; k < 3; ++k) {
+		const View &v = views[k];
+		if (v.rows == 0) continue;
+		std::vector<int32_t> map((size_t)v.rows * n, -1);
+		for (long r = 0; r < v.rows; ++r)
+			for (int32_t t = blob[v.ptr + r]; t < blob[v.ptr + r + 1]; ++t) {
+				const long c = blob[v.col + t];
+				const size_t cell = ordering == ROW_MAJOR_ORDERING ? (size_t)r * n + c : (size_t)c * v.rows + r;
+				map[cell] = (int32_t)(blob[v.val + t] - v.off);
+			}
+		if (!B->d_dense_map[k]) CUDA_TRY(cudaMalloc(&B->d_dense_map[k], map.size() * sizeof(int32_t)));
+		CUDA_TRY(cudaMemcpy(B->d_dense_map[k], map.data(), map.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+	}
+	B->dense_map_ordering = ordering;
+	return 0;
+}
+
 extern "C" {
 
 const char *QPB_LAST_ERROR(void) { return g_last_error.c_str(); }
@@ -507,6 +584,8 @@ void QP_CLEANUP_BATCH(QPBatch *B)
 	cudaFree(B->d_plan);
 	cudaFree(B->d_prog);
 	cudaFree(B->d_stream);
+	for (int k = 0; k < 3; ++k) { cudaFree(B->d_dense_map[k]); cudaFree(B->d_dense[k]); }
+	cudaFree(B->d_violation);
 	cudaFree(B->d_workspace);
 	cudaFree(B->d_spill);
 	cudaFree(B->d_counter);
@@ -541,6 +620,14 @@ qp_int QP_SOLVE_BATCH_DEVICE(QPBatch *B, qp_int count, const settings *opts, con
 qp_int QP_SOLVE_BATCH(QPBatch *B, qp_int count, const settings *opts, const qp_real *Ppr, const qp_real *Apr, const qp_real *Gpr, const qp_real *c, const qp_real *h, const qp_real *b, qp_real *x, qp_real *y, qp_real *z, qp_real *s, qp_int *flag, qp_int *iters)
 {
 	if (!B || !opts || count < 0 || count > B->capacity || !Ppr || !Gpr || !c || !h || (B->plan.p && (!Apr || !b))) return fail(QPB_E_ARG, "QP_SOLVE_BATCH: bad argument", cudaSuccess);
+	return qp_solve_batch_host(B, count, opts, Ppr, Apr, Gpr, c, h, b, x, y, z, s, flag, iters);
+}
+
+} // extern "C"
+
+// Host-pointer solve.  Ppr == nullptr: the value rows P|A|G are in the staging buffers already (dense front-end).
+static qp_int qp_solve_batch_host(QPBatch *B, qp_int count, const settings *opts, const qp_real *Ppr, const qp_real *Apr, const qp_real *Gpr, const qp_real *c, const qp_real *h, const qp_real *b, qp_real *x, qp_real *y, qp_real *z, qp_real *s, qp_int *flag, qp_int *iters)
+{
 	if (count == 0) return 0;
 	std::lock_guard<std::mutex> guard(B->lock);
 	CUDA_TRY(cudaSetDevice(B->device));
@@ -550,7 +637,8 @@ qp_int QP_SOLVE_BATCH(QPBatch *B, qp_int count, const settings *opts, const qp_r
 	cudaStream_t st = B->stream;
 	const size_t n = (size_t)count;
 	const qp_real *src[6] = {Ppr, Apr, Gpr, c, h, b};
-	const size_t widths[6] = {(size_t)pl.nnzP, (size_t)pl.nnzA, (size_t)pl.nnzG, (size_t)pl.n, (size_t)pl.m, (size_t)pl.p};
+	size_t widths[6] = {(size_t)pl.nnzP, (size_t)pl.nnzA, (size_t)pl.nnzG, (size_t)pl.n, (size_t)pl.m, (size_t)pl.p};
+	if (!Ppr) widths[0] = widths[1] = widths[2] = 0; // already on the device
 	BatchIO io;
 	io.Ppr = B->d_in[0]; io.Apr = B->d_in[1]; io.Gpr = B->d_in[2]; io.c = B->d_in[3]; io.h = B->d_in[4]; io.b = B->d_in[5];
 	io.x = B->d_x; io.y = B->d_y; io.z = B->d_z; io.s = B->d_s; io.flag = B->d_flag; io.iters = B->d_iters; io.fval = B->d_fval; io.stat = B->d_stat;
@@ -605,6 +693,60 @@ qp_int QP_SOLVE_BATCH(QPBatch *B, qp_int count, const settings *opts, const qp_r
 		if (B->h_flag[i] != QP_OPTIMAL) ++bad;
 	}
 	return bad;
+}
+
+extern "C" {
+
+qp_int QPB_DENSE_TO_VALUES_DEVICE(QPBatch *B, qp_int count, int ordering, const qp_real *dP, const qp_real *dA, const qp_real *dG, qp_real *dPpr, qp_real *dApr, qp_real *dGpr, int *dviolation, void *stream)
+{
+	if (!B || count < 0 || (ordering != ROW_MAJOR_ORDERING && ordering != COLUMN_MAJOR_ORDERING) || !dP || !dG || !dPpr || !dGpr || (B->plan.p && (!dA || !dApr))) return fail(QPB_E_ARG, "QPB_DENSE_TO_VALUES_DEVICE: bad argument", cudaSuccess);
+	if (count == 0) return 0;
+	CUDA_TRY(cudaSetDevice(B->device));
+	int rc = ensure_dense_maps(B, ordering);
+	if (rc) return rc;
+	const Plan &pl = B->plan;
+	const long grid = (long)B->sm_count * 8;
+	if (dviolation) CUDA_TRY(cudaMemsetAsync(dviolation, 0, (size_t)count * sizeof(int), (cudaStream_t)stream));
+	const long largest = std::max(std::max(pl.n * pl.n, pl.p * pl.n), pl.m * pl.n);
+	const long per_launch = std::max(1L, (1L << 31) / std::max(1L, largest)); // cell numbers stay below 2^31
+	for (long lo = 0; lo < (long)count; lo += per_launch) {
+		const long cnt = std::min(per_launch, (long)count - lo);
+		dense_gather_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(dP, dA, dG, B->d_dense_map[0], B->d_dense_map[1], B->d_dense_map[2], (int)pl.n, (int)pl.m, (int)pl.p, (int)pl.nnzP, (int)pl.nnzA, (int)pl.nnzG, dPpr, dApr, dGpr, dviolation, (int)lo, (int)cnt);
+		CUDA_TRY(cudaGetLastError());
+	}
+	return 0;
+}
+
+qp_int QP_SOLVE_BATCH_DENSE(QPBatch *B, qp_int count, const settings *opts, int ordering, const qp_real *P, const qp_real *A, const qp_real *G, const qp_real *c, const qp_real *h, const qp_real *b, qp_real *x, qp_real *y, qp_real *z, qp_real *s, qp_int *flag, qp_int *iters, qp_int *violation)
+{
+	if (!B || !opts || count < 0 || count > B->capacity || !P || !G || !c || !h || (B->plan.p && (!A || !b))) return fail(QPB_E_ARG, "QP_SOLVE_BATCH_DENSE: bad argument", cudaSuccess);
+	if (count == 0) return 0;
+	std::vector<int> viol((size_t)count, 0);
+	{
+		std::lock_guard<std::mutex> guard(B->lock);
+		CUDA_TRY(cudaSetDevice(B->device));
+		int rc = batch_alloc_staging(B);
+		if (rc) return rc;
+		const Plan &pl = B->plan;
+		const size_t cap = (size_t)B->capacity, n = (size_t)count;
+		const size_t cells[3] = {(size_t)(pl.n * pl.n), (size_t)(pl.p * pl.n), (size_t)(pl.m * pl.n)};
+		const qp_real *src[3] = {P, A, G};
+		cudaStream_t st = B->stream;
+		for (int k = 0; k < 3; ++k) {
+			if (!cells[k]) continue;
+			if (!B->d_dense[k]) CUDA_TRY(cudaMalloc(&B->d_dense[k], cap * cells[k] * sizeof(double)));
+			CUDA_TRY(cudaMemcpyAsync(B->d_dense[k], src[k], n * cells[k] * sizeof(double), cudaMemcpyHostToDevice, st));
+		}
+		if (!B->d_violation) CUDA_TRY(cudaMalloc(&B->d_violation, cap * sizeof(int)));
+		rc = (int)QPB_DENSE_TO_VALUES_DEVICE(B, count, ordering, B->d_dense[0], B->d_dense[1], B->d_dense[2], B->d_in[0], B->d_in[1], B->d_in[2], B->d_violation, st);
+		if (rc) return rc;
+		CUDA_TRY(cudaMemcpyAsync(viol.data(), B->d_violation, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+	}
+	if (violation)
+		for (qp_int i = 0; i < count; ++i) violation[i] = viol[(size_t)i];
+	// the value rows are on the device already: the rest is QP_SOLVE_BATCH without their upload
+	return qp_solve_batch_host(B, count, opts, nullptr, nullptr, nullptr, c, h, b, x, y, z, s, flag, iters);
 }
 
 qp_int QPB_BATCH_SET_SIGMA_D(QPBatch *B, qp_real sigma_d)

@@ -106,6 +106,23 @@ class Batch:
         return (fill(pat.n, pat.Pjc, pat.Pir, self.Ppr[i]), fill(pat.p, pat.Ajc, pat.Air, self.Apr[i]),
                 fill(pat.m, pat.Gjc, pat.Gir, self.Gpr[i]))
 
+    def dense_batch(self, row_major: bool = False):
+        """The whole batch as dense blocks P [count, n*n], A [count, p*n], G [count, m*n], each block column-major
+        (or row-major): the input of ``QP_SOLVE_BATCH_DENSE``."""
+        pat = self.pattern
+
+        def fill(rows, jc, ir, vals):
+            jc, ir = np.asarray(jc), np.asarray(ir)
+            cols = np.repeat(np.arange(pat.n), np.diff(jc))
+            cell = ir * pat.n + cols if row_major else cols * rows + ir
+            M = np.zeros((self.count, rows * pat.n))
+            if cell.size:
+                M[:, cell] = vals
+            return M
+
+        return (fill(pat.n, pat.Pjc, pat.Pir, self.Ppr), fill(pat.p, pat.Ajc, pat.Air, self.Apr),
+                fill(pat.m, pat.Gjc, pat.Gir, self.Gpr))
+
 
 def _ccs_from_mask(mask: np.ndarray):
     cols, rows = np.nonzero(mask.T)  # column-major order of the structural entries

@@ -61,6 +61,7 @@ EXPORTS = [
     "QPB_PLAN_CREATE", "QPB_PLAN_DESTROY", "QPB_PLAN_ARRAY", "QPB_PLAN_INFO", "QPB_AMD_ORDER", "QPB_PLAN_PROGRAM",
     "QPB_PLAN_LAYOUT", "QPB_PLAN_STREAM", "QPB_PLAN_STREAM_INFO", "QPB_PLAN_STREAM_KEY", "QPB_GENERATED_KERNELS",
     "QP_SETUP_BATCH", "QPB_BATCH_CREATE", "QP_SOLVE_BATCH", "QP_SOLVE_BATCH_DEVICE", "QP_CLEANUP_BATCH",
+    "QP_SOLVE_BATCH_DENSE", "QPB_DENSE_TO_VALUES_DEVICE",
     "QPB_BATCH_READ_STATS", "QPB_BATCH_SET_SIGMA_D", "QPB_BATCH_LAST_KERNEL_MS", "QPB_BATCH_LAST_LAUNCHES", "QPB_BATCH_LAST_KERNEL",
     "QPB_LDL_NUMERIC_BATCH", "QPB_LDL_SOLVE_BATCH", "QPB_LAST_ERROR", "QPB_DEVICE_COUNT",
 ]
@@ -113,6 +114,10 @@ def lib():
         lb.QP_SOLVE_BATCH.argtypes = [V, L, C.POINTER(settings)] + [V] * 6 + [V] * 4 + [V, V]
         lb.QP_SOLVE_BATCH_DEVICE.restype = L
         lb.QP_SOLVE_BATCH_DEVICE.argtypes = [V, L, C.POINTER(settings)] + [V] * 6 + [V] * 4 + [V, V, V, V, V]
+        lb.QP_SOLVE_BATCH_DENSE.restype = L
+        lb.QP_SOLVE_BATCH_DENSE.argtypes = [V, L, C.POINTER(settings), C.c_int] + [V] * 6 + [V] * 4 + [V, V, V]
+        lb.QPB_DENSE_TO_VALUES_DEVICE.restype = L
+        lb.QPB_DENSE_TO_VALUES_DEVICE.argtypes = [V, L, C.c_int] + [V] * 8
         lb.QP_CLEANUP_BATCH.argtypes = [V]
         lb.QPB_BATCH_READ_STATS.restype = L
         lb.QPB_BATCH_READ_STATS.argtypes = [V, L, V, V]
@@ -294,6 +299,32 @@ class BatchSolver:
             raise RuntimeError(f"QP_SOLVE_BATCH failed ({rc}): {last_error()}")
         out["not_optimal"] = int(rc)
         return out
+
+    def solve_dense(self, P, A, G, c, h, b, opts: settings | None = None, ordering: int = COLUMN_MAJOR_ORDERING):
+        """``QP_SOLVE_BATCH_DENSE``: dense P [count, n*n], A [count, p*n], G [count, m*n] (each block in the given
+        ordering, as ``QP_SETUP_dense`` takes them), host arrays in and out; also returns the per-QP pattern
+        violation bits (1: nonzero outside the plan's pattern, 2: exact zero inside it)."""
+        pat = self.pattern
+        cnt = int(np.asarray(c).shape[0])
+        opts = opts or default_settings()
+        out = {"x": np.empty((cnt, pat.n)), "y": np.empty((cnt, pat.p)), "z": np.empty((cnt, pat.m)),
+               "s": np.empty((cnt, pat.m)), "flag": np.empty(cnt, dtype=np.int64),
+               "iters": np.empty(cnt, dtype=np.int64), "violation": np.empty(cnt, dtype=np.int64)}
+        arrs = [_f64(a) for a in (P, A, G, c, h, b)]
+        ptr = lambda a: a.ctypes.data if a.size else None
+        rc = lib().QP_SOLVE_BATCH_DENSE(self.handle, cnt, C.byref(opts), int(ordering), *[ptr(a) for a in arrs],
+                                        ptr(out["x"]), ptr(out["y"]), ptr(out["z"]), ptr(out["s"]), ptr(out["flag"]),
+                                        ptr(out["iters"]), ptr(out["violation"]))
+        if rc < 0:
+            raise RuntimeError(f"QP_SOLVE_BATCH_DENSE failed ({rc}): {last_error()}")
+        out["not_optimal"] = int(rc)
+        return out
+
+    def dense_to_values_device(self, count, ordering, dP, dA, dG, dPpr, dApr, dGpr, dviolation=None, stream=None):
+        rc = lib().QPB_DENSE_TO_VALUES_DEVICE(self.handle, int(count), int(ordering), dP, dA, dG, dPpr, dApr, dGpr,
+                                              dviolation, stream)
+        if rc < 0:
+            raise RuntimeError(f"QPB_DENSE_TO_VALUES_DEVICE failed ({rc}): {last_error()}")
 
     def read_stats(self, count: int):
         fval = np.empty(count)

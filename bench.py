@@ -295,6 +295,29 @@ def main():
                 kms = k0.elapsed_time(k1) / args.steps
                 gbs = nbytes * B / (kms * 1e-3) / 1e9
                 kernels[name] = {"ms": kms, "bytes_per_qp": nbytes, "achieved": gbs, "frac": gbs / peak, "per_s": B / (kms * 1e-3)}
+            # dense front-end: dense column-major P | A | G -> plan-ordered value rows.  Bytes: every dense cell read,
+            # every value written once.
+            Bd = B
+            dense = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in batch.slice(0, Bd).dense_batch()]
+            rows_out = [torch.empty((Bd, w), dtype=torch.float64, device=dev) for w in (pat.nnzP, pat.nnzA, pat.nnzG)]
+            viol = torch.empty((Bd,), dtype=torch.int32, device=dev)
+            ptr = lambda t: t.data_ptr() if t.numel() else None
+            fn = lambda: solver.dense_to_values_device(Bd, 30, *[ptr(t) for t in dense], *[ptr(t) for t in rows_out], viol.data_ptr(), st)
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            for _ in range(args.steps):
+                fn()
+            k1.record()
+            torch.cuda.synchronize()
+            kms = k0.elapsed_time(k1) / args.steps
+            nbytes = 8 * (pat.n * pat.n + pat.p * pat.n + pat.m * pat.n + pat.nnzP + pat.nnzA + pat.nnzG) + 4
+            gbs = nbytes * Bd / (kms * 1e-3) / 1e9
+            assert all(torch.equal(r, d) for r, d in zip(rows_out, (devin["Ppr"][:Bd], devin["Apr"][:Bd], devin["Gpr"][:Bd]))) and not bool(viol.any())
+            kernels["dense_gather_kernel"] = {"ms": kms, "qps": Bd, "bytes_per_qp": nbytes, "achieved": gbs, "frac": gbs / peak, "per_s": Bd / (kms * 1e-3)}
+            del dense, rows_out
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "kind": args.kind, "batch_per_gpu": B, "global_batch": world * B, "sharding": f"dp{world} contiguous shards, gather x+flags+iters" if world > 1 else "single GPU",

@@ -125,6 +125,22 @@ qp_int QP_SOLVE_BATCH(QPBatch *batch, qp_int count, const settings *opts, const 
  * [n_rx, n_ry, n_rz, n_mu, alpha_p, alpha_d, sigma, mu] per QP. */
 qp_int QP_SOLVE_BATCH_DEVICE(QPBatch *batch, qp_int count, const settings *opts, const qp_real *dPpr, const qp_real *dApr, const qp_real *dGpr, const qp_real *dc, const qp_real *dh, const qp_real *db, qp_real *dx, qp_real *dy, qp_real *dz, qp_real *ds, int *dflag, int *diters, qp_real *dfval, qp_real *dstat, void *stream);
 
+/* Batched dense front-end.  The controller hands qpSWIFT DENSE matrices (QP_SETUP_dense,
+ * dogbot_controller/src/client/main.cpp:1649-1650; qpSWIFT.c:260-456), which densetosparse /
+ * densetosparse_ROWMAJOR (Auxilary.c:1154-1273) turn into CCS by dropping exact zeros -- a data-dependent
+ * pattern.  A batch has ONE pattern (the plan's); these entries gather, on the device, the value of every
+ * entry of that pattern from dense P [count][n*n], A [count][p*n], G [count][m*n] (ordering =
+ * COLUMN_MAJOR_ORDERING or ROW_MAJOR_ORDERING, GlobalOptions.h:59-60) into the value rows QP_SOLVE_BATCH
+ * takes, and report per QP what the reference's own pattern would have been different in:
+ *   violation bit 0: a nonzero entry lies OUTSIDE the plan's pattern -- the plan does not describe this QP,
+ *                    its solution must not be used;
+ *   violation bit 1: an entry of the pattern is exactly 0.0 -- QP_SETUP_dense would have dropped it and
+ *                    ordered a smaller KKT system (the solution here is that of the explicit pattern).
+ * QPB_DENSE_TO_VALUES_DEVICE: device pointers, asynchronous on `stream`, dviolation (int32) may be NULL.
+ * QP_SOLVE_BATCH_DENSE: host pointers; gather + QP_SOLVE_BATCH; violation[count] may be NULL. */
+qp_int QPB_DENSE_TO_VALUES_DEVICE(QPBatch *batch, qp_int count, int ordering, const qp_real *dP, const qp_real *dA, const qp_real *dG, qp_real *dPpr, qp_real *dApr, qp_real *dGpr, int *dviolation, void *stream);
+qp_int QP_SOLVE_BATCH_DENSE(QPBatch *batch, qp_int count, const settings *opts, int ordering, const qp_real *P, const qp_real *A, const qp_real *G, const qp_real *c, const qp_real *h, const qp_real *b, qp_real *x, qp_real *y, qp_real *z, qp_real *s, qp_int *flag, qp_int *iters, qp_int *violation);
+
 void QP_CLEANUP_BATCH(QPBatch *batch);
 
 /* Device time (ms, CUDA events) of the kernels of the last QP_SOLVE_BATCH call and the number

@@ -173,6 +173,43 @@ def solve_sparse(pat, Ppr, Apr, Gpr, c, h, b, *, kind=None, sigma_d=0.0, permut=
     return sol
 
 
+def solve_dense(n, m, p, P, A, G, c, h, b, *, ordering=30, reltol=None, abstol=None, maxit=None) -> Solution:
+    """``QP_SETUP_dense`` (dense blocks in the given ordering: 30 column-major, 20 row-major) + ``QP_SOLVE`` +
+    ``QP_CLEANUP_dense`` of the compiled reference for ONE instance (dogbot_controller/src/qpSWIFT/qpSWIFT.c:260-456,
+    densetosparse Auxilary.c:1154-1273).  ``plan`` additionally carries the CCS the reference made of the dense
+    input: ``ccs = {"P": (jc, ir, pr), "A": ..., "G": ...}``."""
+    lb = lib("reference")
+    vals = [np.ascontiguousarray(a, dtype=np.float64).ravel().copy() for a in (P, A, G, c, h, b)]
+    has_eq = p > 0
+    qp_p = lb.QP_SETUP_dense(n, m, p, _pd(vals[0]), _pd(vals[1]) if has_eq else None, _pd(vals[2]), _pd(vals[3]),
+                             _pd(vals[4]), _pd(vals[5]) if has_eq else None, None, int(ordering))
+    qp = qp_p.contents
+    o = qp.options.contents
+    if maxit is not None:
+        o.maxit = int(maxit)
+    if reltol is not None:
+        o.reltol = float(reltol)
+    if abstol is not None:
+        o.abstol = float(abstol)
+
+    def ccs(mp, cols):
+        M = mp.contents
+        jc = _arr(M.jc, cols + 1, np.int64)
+        return jc, _arr(M.ir, int(jc[cols]), np.int64), _arr(M.pr, int(jc[cols]), float)
+
+    plan = _plan_of(qp)
+    plan["ccs"] = {"P": ccs(qp.P, n), "G": ccs(qp.G, n)}
+    if has_eq:
+        plan["ccs"]["A"] = ccs(qp.A, n)
+    flag = int(lb.QP_SOLVE(qp_p))
+    st = qp.stats.contents
+    stats = {f: getattr(st, f) for f, _ in Stats._fields_}
+    sol = Solution(_arr(qp.x, qp.n, float), _arr(qp.y, qp.p, float) if has_eq else np.zeros(0), _arr(qp.z, qp.m, float),
+                   _arr(qp.s, qp.m, float), flag, int(st.IterationCount), float(st.fval), stats, plan, {})
+    lb.QP_CLEANUP_dense(qp_p)
+    return sol
+
+
 _GOLDEN_PLANS = None
 
 

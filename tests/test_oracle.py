@@ -62,3 +62,24 @@ def test_golden_solutions_are_kkt_points():
             assert np.linalg.norm(A @ x - b.b[i]) < 1e-6
             assert np.linalg.norm(G @ x + s - b.h[i]) < 1e-6
             assert np.all(s > 0) and np.all(z > 0) and s @ z / len(s) < 1e-6
+
+
+def test_reference_dense_path_is_the_sparse_path_on_dogbot_patterns(oracle):
+    """QP_SETUP_dense drops exact zeros (Auxilary.c:1154-1273); the DogBot blocks have none inside their
+    patterns, so the reference's dense and sparse entries see the same QP -- the premise of the batched dense
+    front-end's parity test (tests/test_dense_gpu.py)."""
+    if not oracle.available("reference"):
+        pytest.skip("needs the compiled reference")
+    for kind in ("trot", "stance"):
+        b = dogbot.generate(kind, 3, start=50)
+        pat = b.pattern
+        for row_major in (False, True):
+            P, A, G = b.dense_batch(row_major=row_major)
+            for i in range(b.count):
+                d = oracle.solve_dense(pat.n, pat.m, pat.p, P[i], A[i], G[i], b.c[i], b.h[i], b.b[i], ordering=20 if row_major else 30)
+                s = oracle.solve_sparse(pat, b.Ppr[i], b.Apr[i], b.Gpr[i], b.c[i], b.h[i], b.b[i], kind="reference")
+                assert np.array_equal(d.plan["ccs"]["G"][1], pat.Gir) and np.array_equal(d.plan["ccs"]["G"][2], b.Gpr[i])
+                assert np.array_equal(d.plan["P"], s.plan["P"])
+                assert (d.flag, d.iters) == (s.flag, s.iters)
+                for k in ("x", "y", "z", "s"):
+                    assert np.array_equal(getattr(d, k), getattr(s, k))
