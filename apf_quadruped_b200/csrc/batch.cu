@@ -143,11 +143,25 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_CTA * 32, 1) qp_solve_cta_kernel
 				ipm_rhs(pv, w.r, w.ds, w.z, w.rhs);
 			}
 		}
+		bool may_leave = true;
 		if (!active) { // next QP: load its value row, set up kkt_initialize's system
 			if (lane == 0) {
-				q = atomicAdd(counter, 1);
-				const int limit = io.count_ptr ? *io.count_ptr : io.count;
-				q = q < limit ? (io.index ? io.index[q] : q) : -1; // the QP behind the ticket
+				if (!io.server_done) {
+					q = atomicAdd(counter, 1);
+					const int limit = io.count_ptr ? *io.count_ptr : io.count;
+					q = q < limit ? (io.index ? io.index[q] : q) : -1; // the QP behind the ticket
+				} else { // server: the list grows while the throughput kernel runs; one attempt per turn, never a wait
+					const int done = *reinterpret_cast<const volatile int *>(io.server_done); // (read before the count)
+					__threadfence();
+					const int limit = *reinterpret_cast<const volatile int *>(io.count_ptr);
+					const int cur = *reinterpret_cast<volatile int *>(counter);
+					q = -1;
+					if (cur < limit) {
+						may_leave = false;
+						const int listed = reinterpret_cast<const volatile int *>(io.index)[cur];
+						if (listed >= 0 && atomicCAS(counter, cur, cur + 1) == cur) q = listed;
+					} else if (!done) may_leave = false;
+				}
 			}
 			q = __shfl_sync(0xffffffffu, q, 0);
 			if (q >= 0) {
@@ -166,7 +180,11 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_CTA * 32, 1) qp_solve_cta_kernel
 				mode = MODE_INIT;
 			}
 		}
-		if (!__syncthreads_or(mode != MODE_IDLE)) break;
+		if (!__syncthreads_or(mode != MODE_IDLE)) {
+			if (!__syncthreads_or(!may_leave)) break;
+			__nanosleep(2000); // a server with nothing listed yet
+			continue;
+		}
 
 		if (mode != MODE_IDLE) {
 			run_segment(pg.words, pg.f_first, pg.f_waves, pg.f_width, sb);
@@ -290,7 +308,8 @@ struct QPBatch
 	double *d_dense[3] = {nullptr, nullptr, nullptr}; // staging of the host-pointer entry
 	int *d_violation = nullptr;
 	cudaStream_t copy_stream = nullptr; // QP_SOLVE_BATCH: the value rows travel while the throughput kernel runs
-	cudaEvent_t ev_go = nullptr;
+	cudaEvent_t ev_go = nullptr, ev_go2 = nullptr, ev_server = nullptr;
+	cudaStream_t aux_stream = nullptr;  // the stragglers' server (latency kernel next to the throughput kernel)
 	int *h_marks = nullptr;             // pinned: the "rows [0, mark) have arrived" values written after each chunk
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	double last_kernel_ms = 0.0;
@@ -358,6 +377,9 @@ static int batch_alloc(QPBatch *B)
 	CUDA_TRY(cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking));
 	CUDA_TRY(cudaStreamCreateWithFlags(&B->copy_stream, cudaStreamNonBlocking));
 	CUDA_TRY(cudaEventCreateWithFlags(&B->ev_go, cudaEventDisableTiming));
+	CUDA_TRY(cudaEventCreateWithFlags(&B->ev_go2, cudaEventDisableTiming));
+	CUDA_TRY(cudaEventCreateWithFlags(&B->ev_server, cudaEventDisableTiming));
+	CUDA_TRY(cudaStreamCreateWithFlags(&B->aux_stream, cudaStreamNonBlocking));
 	CUDA_TRY(cudaMallocHost(&B->h_marks, 256 * sizeof(int)));
 	CUDA_TRY(cudaEventCreate(&B->ev0));
 	CUDA_TRY(cudaEventCreate(&B->ev1));
@@ -410,18 +432,29 @@ static int launch_stream(QPBatch *B, BatchIO io, SolveParams prm, cudaStream_t s
 	const StreamProgram &sp = B->sprog;
 	long slots = std::min(B->stream_slots, ((long)io.count + 31) / 32);
 	const long warps = std::min<long>(B->stream_warps, std::max(1L, (slots + B->sm_count - 1) / B->sm_count));
-	const long grid = (slots + warps - 1) / warps;
 	const size_t smem = (size_t)warps * (sp.lay.scratch + (B->generated ? B->generated->ring_slots : 0)) * 32 * sizeof(double);
 	StreamDims dm;
 	dm.n = (int)B->plan.n; dm.m = (int)B->plan.m; dm.p = (int)B->plan.p; dm.N = (int)B->plan.N;
 	dm.nnzP = (int)B->plan.nnzP; dm.nnzA = (int)B->plan.nnzA; dm.nnzG = (int)B->plan.nnzG;
-	const long spill = getenv("QPB_STREAM_SPILL") ? atol(getenv("QPB_STREAM_SPILL")) : 32;
+	const long spill = getenv("QPB_STREAM_SPILL") ? atol(getenv("QPB_STREAM_SPILL")) : 24;
 	prm.spill_after = spill > 0 && spill < prm.maxit ? (int)spill : 0;
-	int *spill_count = B->d_counter + 48, *second_counter = B->d_counter + 56;
+	int *spill_count = B->d_counter + 48, *second_counter = B->d_counter + 56, *done_ctas = B->d_counter + 57, *all_done = B->d_counter + 58;
+	io.done_ctas = io.all_done = nullptr;
+	// The stragglers' server runs NEXT TO the throughput kernel, on an SM that kernel leaves free (it needs a
+	// whole SM's shared memory); QPB_STREAM_SERVER=0: one launch after the other on the same stream instead.
+	const bool server = prm.spill_after && !(getenv("QPB_STREAM_SERVER") && atoi(getenv("QPB_STREAM_SERVER")) == 0);
+	long grid = (slots + warps - 1) / warps;
 	if (prm.spill_after) {
 		CUDA_TRY(cudaMemsetAsync(spill_count, 0, 16 * sizeof(int), st));
 		io.spill = B->d_spill;
 		io.spill_count = spill_count;
+		if (server) {
+			if (grid >= B->sm_count) { grid = B->sm_count - 1; slots = grid * warps; }
+			CUDA_TRY(cudaMemsetAsync(B->d_spill, 0xff, (size_t)std::min<long>(B->capacity, io.count) * sizeof(int), st));
+			io.done_ctas = done_ctas;
+			io.all_done = all_done;
+			CUDA_TRY(cudaEventRecord(B->ev_go2, st));
+		}
 	}
 	if (B->generated) {
 		int nslots = (int)slots;
@@ -435,14 +468,27 @@ static int launch_stream(QPBatch *B, BatchIO io, SolveParams prm, cudaStream_t s
 	CUDA_TRY(cudaGetLastError());
 	B->last_launches = 1;
 	B->last_kernel = B->generated ? 2 : 1;
-	if (prm.spill_after) { // the stragglers: how many is only known on the device, so the launch is sized for "a few per SM"
+	if (prm.spill_after) { // the stragglers: solved from scratch by the latency kernel, a warp each
 		io.index = B->d_spill;
 		io.count_ptr = spill_count;
 		io.spill = nullptr;
 		io.spill_count = nullptr;
+		io.ready = nullptr;
+		io.done_ctas = nullptr;
+		io.server_done = server ? all_done : nullptr;
+		io.all_done = nullptr;
 		prm.spill_after = 0;
-		const int rc = launch_latency(B, io, prm, (long)B->sm_count * B->max_warps, second_counter, st);
+		cudaStream_t second = st;
+		if (server) { // launched after the throughput kernel (a tool that serialises launches then simply runs it afterwards)
+			second = B->aux_stream;
+			CUDA_TRY(cudaStreamWaitEvent(second, B->ev_go2, 0));
+		}
+		const int rc = launch_latency(B, io, prm, server ? (long)B->max_warps : (long)B->sm_count * B->max_warps, second_counter, second);
 		if (rc) return rc;
+		if (server) {
+			CUDA_TRY(cudaEventRecord(B->ev_server, second));
+			CUDA_TRY(cudaStreamWaitEvent(st, B->ev_server, 0));
+		}
 		B->last_launches = 2;
 	}
 	return 0;
@@ -461,6 +507,8 @@ static int launch_fused(QPBatch *B, BatchIO io, const settings *opts, cudaStream
 	io.count_ptr = nullptr;
 	io.spill = nullptr;
 	io.spill_count = nullptr;
+	io.server_done = nullptr;
+	io.done_ctas = io.all_done = nullptr;
 	if (!(B->d_workspace && io.count >= B->stream_min)) io.ready = nullptr; // only the throughput kernel waits for rows
 	CUDA_TRY(cudaMemsetAsync(B->d_counter, 0, sizeof(int), st));
 	if (B->d_workspace && io.count >= B->stream_min) return launch_stream(B, io, prm, st);
@@ -597,6 +645,9 @@ void QP_CLEANUP_BATCH(QPBatch *B)
 	if (B->stream) cudaStreamDestroy(B->stream);
 	if (B->copy_stream) cudaStreamDestroy(B->copy_stream);
 	if (B->ev_go) cudaEventDestroy(B->ev_go);
+	if (B->ev_go2) cudaEventDestroy(B->ev_go2);
+	if (B->ev_server) cudaEventDestroy(B->ev_server);
+	if (B->aux_stream) cudaStreamDestroy(B->aux_stream);
 	if (B->h_marks) cudaFreeHost(B->h_marks);
 	if (B->ev0) cudaEventDestroy(B->ev0);
 	if (B->ev1) cudaEventDestroy(B->ev1);

@@ -50,6 +50,12 @@ struct BatchIO
 	// throughput kernel behind QP_SOLVE_BATCH: the value rows are still arriving from the host while the kernel
 	// runs; QPs [0, *ready) are there (null: all of them are)
 	const int *ready;
+	// latency kernel as the throughput kernel's straggler SERVER (launched next to it on an SM the throughput
+	// kernel leaves free): QPs appear in index[] (-1 = not written yet) while *count_ptr grows; the server
+	// leaves when *server_done is set and the list is empty (null: the list is complete at launch)
+	const int *server_done;
+	// throughput kernel: where its last warp to leave announces that nothing more will be listed
+	int *done_ctas, *all_done; // (done_ctas counts warps)
 };
 
 #ifdef __CUDACC__

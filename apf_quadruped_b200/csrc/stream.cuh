@@ -261,6 +261,20 @@ static const int STREAM_U = 8; // elements of an elementwise step whose loads ar
 		}                                                              \
 	}
 
+// The last warp of the launch to leave tells the stragglers' server (batch.cu) that the list is complete.
+__device__ __forceinline__ void stream_warp_leaves(const BatchIO &io)
+{
+	if (!io.all_done) return;
+	__syncwarp();
+	if (lane_id() == 0) {
+		__threadfence(); // this warp's entries of the list before its count
+		if (atomicAdd(io.done_ctas, 1) == (int)(gridDim.x * (blockDim.x >> 5)) - 1) {
+			__threadfence();
+			*reinterpret_cast<volatile int *>(io.all_done) = 1;
+		}
+	}
+}
+
 // Where the four micro-programs come from.  InterpretedProgram<G>: the words are fetched from memory
 // and interpreted (run_stream above), whatever the pattern.  A GENERATED program (stream_gen.cuh,
 // apf_quadruped_b200/codegen.py) is the same micro-op sequence of one particular pattern compiled into
@@ -295,7 +309,10 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 	const int lane = lane_id(), warp = threadIdx.x >> 5;
 	const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
 	const bool live = slot < nslots;
-	if (!live && !PROG::cta_sync) return; // (with cta_sync a warp without a tile keeps the CTA's barriers company)
+	if (!live && !PROG::cta_sync) { // (with cta_sync a warp without a tile keeps the CTA's barriers company)
+		stream_warp_leaves(io);
+		return;
+	}
 	double *tile = workspace + (size_t)slot * L.total * 32; // the warp's 32 interleaved slices
 	double *g = tile + lane;
 	const unsigned sb = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)(warp * L.scratch * 32 + lane) * 8u;
@@ -500,6 +517,7 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 		}
 		(void)N;
 	}
+	stream_warp_leaves(io);
 }
 
 #undef SL
