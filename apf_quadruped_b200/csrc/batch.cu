@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_CTA * 32, 1) qp_solve_cta_kernel
 				if (!io.server_done) {
 					q = atomicAdd(counter, 1);
 					const int limit = io.count_ptr ? *io.count_ptr : io.count;
-					q = q < limit ? (io.index ? io.index[q] : q) : -1; // the QP behind the ticket
+					q = q < limit ? (io.index ? io.index[q] : q) : -1; // the QP behind the ticket (| iterations << 24)
 				} else { // server: the list grows while the throughput kernel runs; one attempt per turn, never a wait
 					const int done = *reinterpret_cast<const volatile int *>(io.server_done); // (read before the count)
 					__threadfence();
@@ -160,11 +160,14 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_CTA * 32, 1) qp_solve_cta_kernel
 						may_leave = false;
 						const int listed = reinterpret_cast<const volatile int *>(io.index)[cur];
 						if (listed >= 0 && atomicCAS(counter, cur, cur + 1) == cur) q = listed;
+						__threadfence(); // the entry before what it points at
 					} else if (!done) may_leave = false;
 				}
 			}
 			q = __shfl_sync(0xffffffffu, q, 0);
 			if (q >= 0) {
+				const int resume_at = io.index ? (q >> 24) : 0; // > 0: a straggler's iterate is waiting in the output arrays
+				if (io.index) q &= (1 << 24) - 1;
 				const size_t qi = (size_t)q;
 				warp_copy_in(w.V, io.Ppr + qi * pv.offA, pv.offA);
 				if (p) warp_copy_in(w.V + pv.offA, io.Apr + qi * (pv.offG - pv.offA), pv.offG - pv.offA);
@@ -173,11 +176,26 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_CTA * 32, 1) qp_solve_cta_kernel
 				warp_copy_in(w.h, io.h + qi * m, m);
 				if (p) warp_copy_in(w.b, io.b + qi * p, p);
 				__syncwarp();
-				ipm_init_rhs(pv, w);
-				iters = 0;
-				sigma = prm.sigma0;
-				mu = ap = ad = 0.0;
-				mode = MODE_INIT;
+				if (resume_at > 0 && io.spill_sigma) {
+					// the state of QP_SOLVE's loop between two iterations is (x, y, z, s, sigma, IterationCount);
+					// everything else is recomputed at the top of the next one (qpSWIFT.c:502-552)
+					warp_copy_in(w.x, io.x + qi * n, n);
+					if (p) warp_copy_in(w.y, io.y + qi * p, p);
+					warp_copy_in(w.z, io.z + qi * m, m);
+					warp_copy_in(w.s, io.s + qi * m, m);
+					__syncwarp();
+					iters = resume_at;
+					sigma = io.spill_sigma[q];
+					mu = ap = ad = 0.0;
+					active = true;
+					may_leave = false;
+				} else {
+					ipm_init_rhs(pv, w);
+					iters = 0;
+					sigma = prm.sigma0;
+					mu = ap = ad = 0.0;
+					mode = MODE_INIT;
+				}
 			}
 		}
 		if (!__syncthreads_or(mode != MODE_IDLE)) {
@@ -284,6 +302,7 @@ struct QPBatch
 	uint2 *d_prog = nullptr;
 	int *d_counter = nullptr;
 	int *d_spill = nullptr; // [capacity] QPs the throughput kernel handed over, d_counter[48] = how many
+	double *d_spill_sigma = nullptr; // [capacity] sigma of a handed-over QP
 	ProgramView pview;
 	int max_warps = 1;      // slices of shared memory that fit next to each other in one CTA
 	// throughput kernel (stream.cuh)
@@ -372,6 +391,7 @@ static int batch_alloc(QPBatch *B)
 		const long min_warps = getenv("QPB_STREAM_MIN_WARPS") ? atol(getenv("QPB_STREAM_MIN_WARPS")) : 4;
 		if (B->stream_warps < min_warps) B->stream_min = LONG_MAX;
 		if (B->capacity >= B->stream_min) CUDA_TRY(cudaMalloc(&B->d_spill, (size_t)B->capacity * sizeof(int)));
+		if (B->capacity >= B->stream_min) CUDA_TRY(cudaMalloc(&B->d_spill_sigma, (size_t)B->capacity * sizeof(double)));
 		if (B->capacity >= B->stream_min) CUDA_TRY(cudaMalloc(&B->d_workspace, (size_t)B->stream_slots * sp.lay.total * 32 * sizeof(double)));
 	}
 	CUDA_TRY(cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking));
@@ -448,6 +468,7 @@ static int launch_stream(QPBatch *B, BatchIO io, SolveParams prm, cudaStream_t s
 		CUDA_TRY(cudaMemsetAsync(spill_count, 0, 16 * sizeof(int), st));
 		io.spill = B->d_spill;
 		io.spill_count = spill_count;
+		io.spill_sigma = getenv("QPB_STREAM_RESTART") ? nullptr : B->d_spill_sigma; // QPB_STREAM_RESTART=1: stragglers start from scratch
 		if (server) {
 			if (grid >= B->sm_count) { grid = B->sm_count - 1; slots = grid * warps; }
 			CUDA_TRY(cudaMemsetAsync(B->d_spill, 0xff, (size_t)std::min<long>(B->capacity, io.count) * sizeof(int), st));
@@ -507,6 +528,7 @@ static int launch_fused(QPBatch *B, BatchIO io, const settings *opts, cudaStream
 	io.count_ptr = nullptr;
 	io.spill = nullptr;
 	io.spill_count = nullptr;
+	io.spill_sigma = nullptr;
 	io.server_done = nullptr;
 	io.done_ctas = io.all_done = nullptr;
 	if (!(B->d_workspace && io.count >= B->stream_min)) io.ready = nullptr; // only the throughput kernel waits for rows
@@ -632,6 +654,7 @@ void QP_CLEANUP_BATCH(QPBatch *B)
 	cudaFree(B->d_plan);
 	cudaFree(B->d_prog);
 	cudaFree(B->d_stream);
+	cudaFree(B->d_spill_sigma);
 	for (int k = 0; k < 3; ++k) { cudaFree(B->d_dense_map[k]); cudaFree(B->d_dense[k]); }
 	cudaFree(B->d_violation);
 	cudaFree(B->d_workspace);

@@ -47,6 +47,9 @@ struct BatchIO
 	const int *index;     // null: QP i is QP i
 	const int *count_ptr; // null: count
 	int *spill, *spill_count; // throughput kernel: where it lists the QPs it hands over (null: it never does)
+	// hand-over of a straggler's iterate: x, y, z, s travel through the output arrays, the iteration count in the
+	// list entry (QP | iterations << 24), sigma here (null: stragglers are restarted from scratch)
+	double *spill_sigma;
 	// throughput kernel behind QP_SOLVE_BATCH: the value rows are still arriving from the host while the kernel
 	// runs; QPs [0, *ready) are there (null: all of them are)
 	const int *ready;

@@ -358,11 +358,7 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 			}
 		}
 		// ---- QPs that leave the loop: the warp writes them back, one finished lane at a time --------
-		if (active && flag == 4) {
-			io.spill[atomicAdd(io.spill_count, 1)] = q;
-			active = false;
-			flag = -1;
-		}
+		// (a straggler, flag 4, leaves its iterate in the output arrays too: the latency kernel resumes from it)
 		unsigned done = __ballot_sync(FULL, active && flag >= 0);
 		__syncwarp();
 		while (done) {
@@ -370,12 +366,21 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 			done &= done - 1;
 			const size_t qi = (size_t)__shfl_sync(FULL, q, src);
 			const double *from = tile + src;
-			if (io.x) for (int e = lane; e < n; e += 32) io.x[qi * n + e] = from[(L.x + e) << 5];
-			if (io.y) for (int e = lane; e < p; e += 32) io.y[qi * p + e] = from[(L.y + e) << 5];
-			if (io.z) for (int e = lane; e < m; e += 32) io.z[qi * m + e] = from[(L.z + e) << 5];
-			if (io.s) for (int e = lane; e < m; e += 32) io.s[qi * m + e] = from[(L.s + e) << 5];
+			if (io.x) stream_give_row(io.x + qi * n, from + ((size_t)L.x << 5), n, lane);
+			if (io.y) stream_give_row(io.y + qi * p, from + ((size_t)L.y << 5), p, lane);
+			if (io.z) stream_give_row(io.z + qi * m, from + ((size_t)L.z << 5), m, lane);
+			if (io.s) stream_give_row(io.s + qi * m, from + ((size_t)L.s << 5), m, lane);
 		}
-		if (active && flag >= 0) {
+		__syncwarp();
+		if (active && flag == 4) {
+			// list entry: QP | iterations << 24 when the iterate is handed over (all of x, z, s[, y] are written and
+			// the batch is small enough for 24 bits), else the bare QP: the latency kernel starts it from scratch
+			const bool hand_over = io.spill_sigma && io.x && io.z && io.s && (p == 0 || io.y) && io.count < (1 << 24) && iters < 128;
+			if (hand_over) io.spill_sigma[q] = sigma;
+			__threadfence(); // the iterate before the entry
+			io.spill[atomicAdd(io.spill_count, 1)] = hand_over ? (q | (iters << 24)) : q;
+			active = false;
+		} else if (active && flag >= 0) {
 			if (io.flag) io.flag[q] = flag;
 			if (io.iters) io.iters[q] = iters;
 			if (io.fval) io.fval[q] = sc.fval;
