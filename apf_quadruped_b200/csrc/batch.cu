@@ -718,6 +718,22 @@ static qp_int qp_solve_batch_host(QPBatch *B, qp_int count, const settings *opts
 	io.x = B->d_x; io.y = B->d_y; io.z = B->d_z; io.s = B->d_s; io.flag = B->d_flag; io.iters = B->d_iters; io.fval = B->d_fval; io.stat = B->d_stat;
 	io.count = (int)count;
 	io.ready = nullptr;
+	// Results straight into the caller's buffers where those are page-locked (and therefore mapped into the
+	// device's address space): the throughput kernel writes a finished QP's rows 256 bytes at a time over the
+	// bus while the others are still being solved, instead of one copy of everything after the kernel.
+	bool direct[4] = {false, false, false, false};
+	if (B->d_workspace && count >= B->stream_min && !getenv("QPB_NO_OVERLAP")) {
+		qp_real *host_out[4] = {x, y, z, s};
+		double **dev_out[4] = {&io.x, &io.y, &io.z, &io.s};
+		for (int k = 0; k < 4; ++k) {
+			if (!host_out[k] || (k == 1 && !pl.p)) continue;
+			cudaPointerAttributes attr;
+			if (cudaPointerGetAttributes(&attr, host_out[k]) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+				*dev_out[k] = static_cast<double *>(attr.devicePointer);
+				direct[k] = true;
+			} else cudaGetLastError(); // (an unregistered pointer is not an error here)
+		}
+	}
 	const bool overlap = B->d_workspace && count >= B->stream_min && !getenv("QPB_NO_OVERLAP");
 	if (!overlap) {
 		for (int i = 0; i < 6; ++i)
@@ -750,10 +766,10 @@ static qp_int qp_solve_batch_host(QPBatch *B, qp_int count, const settings *opts
 		if (rc) return rc;
 	}
 	CUDA_TRY(cudaEventRecord(B->ev1, st));
-	if (x) CUDA_TRY(cudaMemcpyAsync(x, B->d_x, n * pl.n * sizeof(double), cudaMemcpyDeviceToHost, st));
-	if (y && pl.p) CUDA_TRY(cudaMemcpyAsync(y, B->d_y, n * pl.p * sizeof(double), cudaMemcpyDeviceToHost, st));
-	if (z) CUDA_TRY(cudaMemcpyAsync(z, B->d_z, n * pl.m * sizeof(double), cudaMemcpyDeviceToHost, st));
-	if (s) CUDA_TRY(cudaMemcpyAsync(s, B->d_s, n * pl.m * sizeof(double), cudaMemcpyDeviceToHost, st));
+	if (x && !direct[0]) CUDA_TRY(cudaMemcpyAsync(x, B->d_x, n * pl.n * sizeof(double), cudaMemcpyDeviceToHost, st));
+	if (y && pl.p && !direct[1]) CUDA_TRY(cudaMemcpyAsync(y, B->d_y, n * pl.p * sizeof(double), cudaMemcpyDeviceToHost, st));
+	if (z && !direct[2]) CUDA_TRY(cudaMemcpyAsync(z, B->d_z, n * pl.m * sizeof(double), cudaMemcpyDeviceToHost, st));
+	if (s && !direct[3]) CUDA_TRY(cudaMemcpyAsync(s, B->d_s, n * pl.m * sizeof(double), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaMemcpyAsync(B->h_flag, B->d_flag, n * sizeof(int), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaMemcpyAsync(B->h_iters, B->d_iters, n * sizeof(int), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));

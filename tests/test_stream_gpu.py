@@ -119,3 +119,28 @@ def test_stragglers_are_handed_to_the_latency_kernel(qps, oracle, stream_only, m
     fval, stat = solver.read_stats(256)
     assert np.array_equal(fval, ref["fval"])
     solver.close()
+
+
+def test_results_written_straight_into_pinned_buffers(qps, oracle, stream_only):
+    """QP_SOLVE_BATCH lets the throughput kernel write finished rows directly into page-locked caller buffers
+    (no staging copy); pageable buffers take the staged path.  Same bits either way, stragglers included."""
+    import torch
+    batch = dogbot.generate("trot", 700, start=264000)  # contains the maxit instance 264420
+    solver = qps.BatchSolver(batch.pattern, batch.count)
+    plain = solver.solve(batch)
+    pat = batch.pattern
+    pinned = {"x": torch.empty((batch.count, pat.n), dtype=torch.float64).pin_memory(),
+              "y": torch.empty((batch.count, pat.p), dtype=torch.float64).pin_memory(),
+              "z": torch.empty((batch.count, pat.m), dtype=torch.float64).pin_memory(),
+              "s": torch.empty((batch.count, pat.m), dtype=torch.float64).pin_memory()}
+    out = {k: v.numpy() for k, v in pinned.items()}
+    out["flag"] = np.empty(batch.count, dtype=np.int64)
+    out["iters"] = np.empty(batch.count, dtype=np.int64)
+    for v in pinned.values():
+        v.fill_(float("nan"))
+    solver.solve(batch, out=out)
+    for k in ("x", "y", "z", "s", "flag", "iters"):
+        assert np.array_equal(out[k], plain[k]), k
+    assert out["iters"].max() == 100
+    check_against_oracle(plain, oracle.solve_batch(batch))
+    solver.close()
