@@ -15,6 +15,8 @@ WHERE a value waits for its next use:
   the same element);
 * an operand that was loaded or stored at most `reuse` micro-ops ago is taken from its register instead
   of HBM; constants (+0.0, 1.0, -1.0) are literals;
+* residual products: an entry of G or A feeds two chains ((G x)_k and (G'z)_i); the chains are interleaved so
+  that both take it from one load (`share`);
 * LDL_numeric: up to `rows` consecutive rows of L are computed TOGETHER (their chains interleaved), so
   that the entries of L they both read are fetched once; the row-local work vectors Y of these rows
   live in registers (every index is known) as far as `ybudget` doubles go, and in disjoint parts of
@@ -41,7 +43,7 @@ import numpy as np
 TERM, DIVACC, DIV, INITD, ENDD, LOADS, NOP = 0, 2, 3, 4, 5, 6, 8
 FIRSTZ, INIT, ST_SHARED, ST_HBM, LATE1, ONE, SLOW = (1 << (52 + i) for i in range(7))
 
-DEFAULTS = dict(dist=24, reuse=16, chunk=256, rows=3, ybudget=60, fn_ops=400, block_ops=4000, sync=1000000, pdist=0, ring=0, group=4, ahead=6)
+DEFAULTS = dict(dist=24, reuse=16, chunk=256, rows=3, ybudget=60, fn_ops=400, block_ops=4000, sync=1000000, pdist=0, ring=0, group=4, ahead=6, share=1)
 
 
 class Op:
@@ -348,6 +350,77 @@ def build_factor(B: Builder, ops):
     B.fn = None
 
 
+def build_shared_chains(B: Builder, ops):
+    """Residual products: a matrix entry is used by two chains (G(k,i) in (G x)_k and in (G'z)_i, A likewise).
+    Every chain keeps its own order; a chain whose next term wants the element the leading chain has just
+    loaded takes its term right behind it (one load for both), and a chain that shares nothing any more is
+    finished on the spot, so that its accumulator does not stay around.  Returns False (nothing emitted) when
+    the program is not a set of independent multiply-subtract chains."""
+    chains = []
+    for o in ops:
+        if o.op not in (TERM, NOP) or (o.w & ST_SHARED):
+            return False
+        if not chains or (o.op == TERM and (o.w & (FIRSTZ | INIT))):
+            chains.append([])
+        chains[-1].append(o)
+    where = {}
+    for ci, ch in enumerate(chains):
+        for o in ch:
+            if o.w & ST_HBM:
+                where.setdefault(o.c, set()).add(ci)
+    for ci, ch in enumerate(chains):  # a chain may only load what it stores itself
+        if any(o.uses_p and where.get(o.f1, {ci}) != {ci} for o in ch):
+            return False
+    uses = {}
+    for ch in chains:
+        for o in ch:
+            if o.uses_p:
+                uses[o.f1] = uses.get(o.f1, 0) + 1
+    if not any(v > 1 for v in uses.values()):
+        return False
+    B.begin(False)
+    nxt = [0] * len(chains)
+    acc = [None] * len(chains)
+
+    def emit(ci):
+        o = chains[ci][nxt[ci]]
+        nxt[ci] += 1
+        P = B.operand(o.f1) if o.uses_p else None
+        if o.uses_p:
+            uses[o.f1] -= 1
+        S = B.lds(o.f2) if o.uses_s else None
+        if o.op == TERM:
+            if o.w & INIT:
+                acc[ci] = P
+            else:
+                v = B.var("t")
+                B.put(("msub", v, "0.0" if o.w & FIRSTZ else acc[ci], P, None if o.w & ONE else S))
+                acc[ci] = v
+        if o.w & ST_HBM:
+            B.stg(o.c, acc[ci])
+        B.step()
+
+    def private(ci):
+        return all(not o.uses_p or uses[o.f1] == 1 for o in chains[ci][nxt[ci]:])
+
+    for lead in range(len(chains)):
+        while nxt[lead] < len(chains[lead]):
+            o = chains[lead][nxt[lead]]
+            emit(lead)
+            if not o.uses_p or uses[o.f1] == 0:
+                continue
+            for ci in range(len(chains)):
+                if ci != lead and nxt[ci] < len(chains[ci]):
+                    n = chains[ci][nxt[ci]]
+                    if n.uses_p and n.f1 == o.f1:
+                        emit(ci)
+                        if nxt[ci] > 0 and private(ci):
+                            while nxt[ci] < len(chains[ci]):
+                                emit(ci)
+    B.fn = None
+    return True
+
+
 def add_l2_prefetch(B: Builder):
     """Every HBM load is announced `pdist` micro-ops ahead by a prefetch into L2 (no register, no
     scoreboard, may sit in an earlier function): the load itself then finds its line in L2."""
@@ -368,7 +441,7 @@ def build_segment(seg, ops, consts, opt, scratch):
     B = Builder(seg, consts, opt, scratch)
     if seg == "factor" and opt["rows"] > 0:
         build_factor(B, ops)
-    else:
+    elif not (seg in ("resid", "resz") and opt["share"] and build_shared_chains(B, ops)):
         B.generic_run(ops)
     add_l2_prefetch(B)
     return B

@@ -16,7 +16,7 @@ def same(a, b):
     return np.array_equal(a, b, equal_nan=True) and np.array_equal(np.signbit(a), np.signbit(b))
 
 
-@pytest.mark.parametrize("options", [{}, {"ring": 0}, {"ring": 8, "group": 3, "ahead": 2, "dist": 40}, {"rows": 2, "reuse": 16, "dist": 8}, {"rows": 0}, {"ybudget": 12, "fn_ops": 50, "chunk": 37, "rows": 4}])
+@pytest.mark.parametrize("options", [{}, {"share": 0}, {"ring": 8, "group": 3, "ahead": 2, "dist": 40}, {"rows": 2, "reuse": 16, "dist": 8}, {"rows": 0}, {"ybudget": 12, "fn_ops": 50, "chunk": 37, "rows": 4}])
 @pytest.mark.parametrize("kind", ["trot", "stance", "crawl", "mpc"])
 def test_ir_leaves_the_slice_as_the_program_does(qps, kind, options):
     batch = dogbot.generate(kind, 2, start=4242)
