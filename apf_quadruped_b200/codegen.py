@@ -43,7 +43,7 @@ import numpy as np
 TERM, DIVACC, DIV, INITD, ENDD, LOADS, NOP = 0, 2, 3, 4, 5, 6, 8
 FIRSTZ, INIT, ST_SHARED, ST_HBM, LATE1, ONE, SLOW = (1 << (52 + i) for i in range(7))
 
-DEFAULTS = dict(dist=24, reuse=16, chunk=256, rows=3, ybudget=60, fn_ops=400, block_ops=4000, sync=1000000, pdist=0, ring=0, group=4, ahead=6, share=1)
+DEFAULTS = dict(dist=24, reuse=16, chunk=256, rows=3, ybudget=60, fn_ops=400, block_ops=4000, pdist=0, ring=0, group=4, ahead=6, share=1)
 
 
 class Op:
@@ -606,10 +606,10 @@ def evaluate(B: Builder, G, S):
 
 def print_cuda(B: Builder, out, div):
     """Every function takes `mine` (does this warp have work here?) and is entered by ALL warps of the
-    CTA: they meet at a barrier every `sync` micro-ops, so that they fetch the same instructions at about
-    the same time (the code is far larger than the instruction caches), and a warp with nothing to do
-    skips the work between the barriers."""
-    sync = B.opt["sync"]
+    CTA: they meet at a barrier at its top, so that they fetch the same instructions at about the same
+    time (the code is far larger than the instruction caches), and a warp with nothing to do skips the
+    work.  (Barriers INSIDE a function -- `if (mine) {...}` blocks -- were measured and lose 30 %: values
+    that live across the blocks get spilled.)"""
     for fn in B.functions:
         if fn.carried:
             out.append(f"static __device__ __noinline__ double2 {fn.name}(char *g, const unsigned sb, const unsigned rb, const bool mine, const double t_in, const double d_in)\n{{")

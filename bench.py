@@ -13,13 +13,15 @@ is the gather of solutions and exit flags the north_star names).
              max over ranks.
   e2e        the same metric through the reference-facing C ABI call QP_SOLVE_BATCH with HOST
              buffers (pinned): H2D of the value rows and D2H of x, y, z, s, flags, iterations inside
-             the timed region.
+             the timed region (the library sends the rows up in chunks while the kernel already runs and
+             lets the kernel write finished rows straight into the pinned result buffers; the bytes are
+             the same, and the results are checked against the device-pointer path).
   roofline   dominant kernel (the throughput kernel qp_solve_stream_kernel: one QP per thread, working
              sets interleaved in HBM) against the measured HBM peak: "achieved" uses SURVEY.md section
              8d's ALGORITHMIC bytes per solve (see DESIGN.md "roofline"), "traffic" is the kernel's real
              DRAM traffic per launch from the committed ncu capture (profiles/ncu_traffic.json), and
              "traffic_gbs" that traffic over the live launch time; plus the stand-alone LDL factor /
-             solve kernels under "kernels".
+             solve kernels and the dense front-end's gather kernel under "kernels".
   cpu_baseline  the reference qpSWIFT (oracle/_ref, kind "reference"; else our port) on the box's
              host cores, one instance per thread, on a bounded sample of the same workload.
 
