@@ -442,11 +442,12 @@ static int launch_latency(QPBatch *B, const BatchIO &io, const SolveParams &prm,
 }
 
 // Large batches: one thread per QP (stream.cuh).  One CTA per SM, stream_warps warps each.  A QP that
-// needs far more iterations than its neighbours (the ~1 % of trot QPs that run into maxit = 100) would keep
+// needs far more iterations than its neighbours (the rare trot QP that runs into maxit = 100) would keep
 // its warp -- and the launch -- alive long after the batch is done, at one thread's pace; the throughput
-// kernel therefore hands every QP that has not converged after QPB_STREAM_SPILL iterations (default 32)
-// over to the latency kernel, which solves those few from scratch with a warp each.  Results do not
-// depend on which kernel produced them (both are bit-identical with the reference).
+// kernel therefore hands every QP that has not converged after QPB_STREAM_SPILL iterations (default 24)
+// over to the latency kernel, a warp each, together with its iterate (x, y, z, s, sigma, iteration count:
+// the complete state of QP_SOLVE's loop between two iterations), so that nothing is solved twice.  Results
+// do not depend on which kernel produced them (both are bit-identical with the reference).
 static int launch_stream(QPBatch *B, BatchIO io, SolveParams prm, cudaStream_t st)
 {
 	const StreamProgram &sp = B->sprog;
