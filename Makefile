@@ -44,6 +44,7 @@ $(OBJ)/gen_%.cu.o: $(GEN)/%.cu $(wildcard $(SRC)/*.h $(SRC)/*.cuh) $(wildcard in
 
 gen:
 	python -m apf_quadruped_b200.codegen --out $(GEN) $(GEN_KINDS)
+	python -m apf_quadruped_b200.codegen_warp --out $(GEN) $(GEN_KINDS)
 
 $(LIB): $(HOST_OBJS) $(CU_OBJS) $(GEN_OBJS)
 	@mkdir -p $(dir $(LIB))

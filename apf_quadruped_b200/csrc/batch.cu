@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "stream.cuh"
 #include "stream_gen.cuh"
+#include "warp_kernel.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -53,6 +54,23 @@ int list_generated_kernels(unsigned long long *keys, int capacity)
 	return (int)v.size();
 }
 
+// ... and the pattern-specialised warp-per-QP kernels (warp_kernel.cuh, codegen_warp.py)
+static std::vector<GeneratedWarpKernel> &generated_warp_kernels()
+{
+	static std::vector<GeneratedWarpKernel> v;
+	return v;
+}
+void register_generated_warp_kernel(unsigned long long key, const void *kernel, const void *kernel_free, const char *name, const SliceLayout &lay)
+{
+	generated_warp_kernels().push_back(GeneratedWarpKernel{key, kernel, kernel_free, name, lay});
+}
+const GeneratedWarpKernel *find_generated_warp_kernel(unsigned long long key)
+{
+	for (const GeneratedWarpKernel &k : generated_warp_kernels())
+		if (k.key == key) return &k;
+	return nullptr;
+}
+
 static int fail(int code, const char *what, cudaError_t e)
 {
 	char buf[256];
@@ -70,171 +88,6 @@ static int fail(int code, const char *what, cudaError_t e)
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-
-struct ProgramView
-{
-	const uint2 *words;
-	int f_first, f_waves, f_width, s_first, s_waves, s_width;
-};
-
-enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_PRED = 2, MODE_CENT = 3 };
-static const int MAX_WARPS_PER_CTA = 16;
-
-__global__ void __launch_bounds__(MAX_WARPS_PER_CTA * 32, 1) qp_solve_cta_kernel(const int *__restrict__ plan, ProgramView pg, SliceLayout lay, BatchIO io, SolveParams prm, int *__restrict__ counter)
-{
-	extern __shared__ __align__(16) double smem[];
-	const PlanView pv = view_of(plan);
-	const int lane = lane_id(), warp = threadIdx.x >> 5;
-	double *S = smem + (size_t)warp * lay.total;
-	const unsigned sb = (unsigned)__cvta_generic_to_shared(S);
-	WarpState w = carve(S, lay);
-	if (lane == 0) { S[lay.zero] = 0.0; S[lay.zero + 1] = -0.0; }
-	__syncwarp();
-	const int n = pv.n, m = pv.m, p = pv.p;
-	const double thr = prm.reltol / sqrt(3.0);
-
-	int q = 0, iters = 0;
-	bool active = false; // a QP is between its initial point and its exit
-	double sigma = 0.0, mu = 0.0, ap = 0.0, ad = 0.0;
-	Scalars sc;
-	sc.n_rx = sc.n_ry = sc.n_rz = sc.n_mu = sc.fval = 0.0;
-
-	for (;;) {
-		int mode = MODE_IDLE;
-		if (active) { // top of QP_SOLVE's loop (qpSWIFT.c:502-534)
-			int flag = -1;
-			if (iters >= prm.maxit) flag = 2; // QP_MAXIT (qpSWIFT.c:604-607)
-			else {
-				sc = ipm_residuals(pv, w.V, w.c, w.h, w.b, w.x, w.y, w.z, w.s, w.r, w.lam /* scratch: -(Px) */);
-				if (sc.n_rx < thr && sc.n_rz < thr && (p == 0 || sc.n_ry < thr) && sc.n_mu < prm.abstol) flag = 0;
-			}
-			if (flag >= 0) {
-				const size_t qi = (size_t)q;
-				warp_copy_out(io.x ? io.x + qi * n : nullptr, w.x, n);
-				if (p) warp_copy_out(io.y ? io.y + qi * p : nullptr, w.y, p);
-				warp_copy_out(io.z ? io.z + qi * m : nullptr, w.z, m);
-				warp_copy_out(io.s ? io.s + qi * m : nullptr, w.s, m);
-				if (lane == 0) {
-					if (io.flag) io.flag[q] = flag;
-					if (io.iters) io.iters[q] = iters;
-					if (io.fval) io.fval[q] = sc.fval;
-					if (io.stat) {
-						double *st = io.stat + qi * 8;
-						st[0] = sc.n_rx; st[1] = sc.n_ry; st[2] = sc.n_rz; st[3] = sc.n_mu;
-						st[4] = ap; st[5] = ad; st[6] = sigma; st[7] = mu;
-					}
-				}
-				__syncwarp();
-				active = false;
-			} else {
-				__syncwarp();
-				mu = ipm_lambda_mu(m, w);
-				if (sigma > prm.sigma_d) { // predictor: ds = -lambda^2 (qpSWIFT.c:540-552)
-					for (int i = lane; i < m; i += 32) w.ds[i] = -w.lam[i] * w.lam[i];
-					mode = MODE_PRED;
-				} else {                   // centering step only (qpSWIFT.c:572-579)
-					sigma = prm.sigma_d;
-					const double sm = sigma * mu;
-					for (int i = lane; i < m; i += 32) w.ds[i] = -(w.lam[i] * w.lam[i]) + sm;
-					mode = MODE_CENT;
-				}
-				ipm_update_kkt(m, w);
-				__syncwarp();
-				ipm_rhs(pv, w.r, w.ds, w.z, w.rhs);
-			}
-		}
-		bool may_leave = true;
-		if (!active) { // next QP: load its value row, set up kkt_initialize's system
-			if (lane == 0) {
-				if (!io.server_done) {
-					q = atomicAdd(counter, 1);
-					const int limit = io.count_ptr ? *io.count_ptr : io.count;
-					q = q < limit ? (io.index ? io.index[q] : q) : -1; // the QP behind the ticket (| iterations << 24)
-				} else { // server: the list grows while the throughput kernel runs; one attempt per turn, never a wait
-					const int done = *reinterpret_cast<const volatile int *>(io.server_done); // (read before the count)
-					__threadfence();
-					const int limit = *reinterpret_cast<const volatile int *>(io.count_ptr);
-					const int cur = *reinterpret_cast<volatile int *>(counter);
-					q = -1;
-					if (cur < limit) {
-						may_leave = false;
-						const int listed = reinterpret_cast<const volatile int *>(io.index)[cur];
-						if (listed >= 0 && atomicCAS(counter, cur, cur + 1) == cur) q = listed;
-						__threadfence(); // the entry before what it points at
-					} else if (!done) may_leave = false;
-				}
-			}
-			q = __shfl_sync(0xffffffffu, q, 0);
-			if (q >= 0) {
-				const int resume_at = io.index ? (q >> 24) : 0; // > 0: a straggler's iterate is waiting in the output arrays
-				if (io.index) q &= (1 << 24) - 1;
-				const size_t qi = (size_t)q;
-				warp_copy_in(w.V, io.Ppr + qi * pv.offA, pv.offA);
-				if (p) warp_copy_in(w.V + pv.offA, io.Apr + qi * (pv.offG - pv.offA), pv.offG - pv.offA);
-				warp_copy_in(w.V + pv.offG, io.Gpr + qi * (pv.nV - pv.offG), pv.nV - pv.offG);
-				warp_copy_in(w.c, io.c + qi * n, n);
-				warp_copy_in(w.h, io.h + qi * m, m);
-				if (p) warp_copy_in(w.b, io.b + qi * p, p);
-				__syncwarp();
-				if (resume_at > 0 && io.spill_sigma) {
-					// the state of QP_SOLVE's loop between two iterations is (x, y, z, s, sigma, IterationCount);
-					// everything else is recomputed at the top of the next one (qpSWIFT.c:502-552)
-					warp_copy_in(w.x, io.x + qi * n, n);
-					if (p) warp_copy_in(w.y, io.y + qi * p, p);
-					warp_copy_in(w.z, io.z + qi * m, m);
-					warp_copy_in(w.s, io.s + qi * m, m);
-					__syncwarp();
-					iters = resume_at;
-					sigma = io.spill_sigma[q];
-					mu = ap = ad = 0.0;
-					active = true;
-					may_leave = false;
-				} else {
-					ipm_init_rhs(pv, w);
-					iters = 0;
-					sigma = prm.sigma0;
-					mu = ap = ad = 0.0;
-					mode = MODE_INIT;
-				}
-			}
-		}
-		if (!__syncthreads_or(mode != MODE_IDLE)) {
-			if (!__syncthreads_or(!may_leave)) break;
-			__nanosleep(2000); // a server with nothing listed yet
-			continue;
-		}
-
-		if (mode != MODE_IDLE) {
-			run_segment(pg.words, pg.f_first, pg.f_waves, pg.f_width, sb);
-			run_segment(pg.words, pg.s_first, pg.s_waves, pg.s_width, sb);
-		}
-		if (mode == MODE_INIT) {
-			ipm_init_point(pv, w);
-			active = true;
-		} else if (mode == MODE_PRED) { // affine step length, sigma, corrector right-hand side (qpSWIFT.c:564-570)
-			ipm_recover_dz_ds(pv, w);
-			ipm_steplength(m, w.s, w.dsl, w.z, w.dz, ap, ad);
-			sigma = ipm_sigma(m, w, ap, ad, prm.sigma_d);
-			const double sm = sigma * mu;
-			for (int i = lane; i < m; i += 32) w.ds[i] = -(w.lam[i] * w.lam[i]) - (w.dsl[i] * w.dz[i]) + sm;
-			__syncwarp();
-			ipm_rhs(pv, w.r, w.ds, w.z, w.rhs);
-		}
-		__syncthreads(); // re-align the warps before they stream the solve schedule again
-		if (mode == MODE_PRED) run_segment(pg.words, pg.s_first, pg.s_waves, pg.s_width, sb);
-		if (mode == MODE_PRED || mode == MODE_CENT) { // step, damping, update (qpSWIFT.c:584-596)
-			ipm_recover_dz_ds(pv, w);
-			ipm_steplength(m, w.s, w.dsl, w.z, w.dz, ap, ad);
-			ap = ((0.99 * ap) < (1.0)) ? (0.99 * ap) : (1.0);
-			ad = ((0.99 * ad) < (1.0)) ? (0.99 * ad) : (1.0);
-			for (int i = lane; i < n; i += 32) w.x[i] += w.rhs[i] * ap;
-			for (int i = lane; i < p; i += 32) w.y[i] += w.rhs[n + i] * ad;
-			for (int i = lane; i < m; i += 32) { w.s[i] += w.dsl[i] * ap; w.z[i] += w.dz[i] * ad; }
-			__syncwarp();
-			++iters;
-		}
-	}
-}
 
 // LDL_numeric alone: value row + (z,z) diagonal from HBM, factor to HBM.  One warp per CTA.
 __global__ void __launch_bounds__(32) ldl_numeric_kernel(const int *__restrict__ plan, ProgramView pg, SliceLayout lay, const double *__restrict__ vals, const double *__restrict__ zdiag, double *__restrict__ Lx, double *__restrict__ D, int count, int *__restrict__ counter)
@@ -314,6 +167,8 @@ struct QPBatch
 	long stream_slots = 0;  // warps in flight on the device = tiles of 32 slices in the workspace
 	long stream_min = 0;    // smallest batch that goes to the throughput kernel
 	const GeneratedKernel *generated = nullptr; // the pattern's specialised kernel, if the library carries one
+	const GeneratedWarpKernel *gen_warp = nullptr; // the pattern's specialised warp-per-QP kernel, if the library carries one
+	int gen_warps = 0;      // warps per CTA of that kernel
 	size_t smem_limit = 0;
 	// device staging for the host-pointer entry point
 	double *d_in[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -333,7 +188,7 @@ struct QPBatch
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	double last_kernel_ms = 0.0;
 	long last_launches = 0;
-	int last_kernel = 0; // 0 latency kernel (one QP per warp), 1 throughput kernel (one QP per thread), 2 the same, pattern-specialised
+	int last_kernel = 0; // 0 warp-per-QP kernel (interpreted schedules), 1 throughput kernel (one QP per thread), 2 the same, pattern-specialised, 3 warp-per-QP kernel, pattern-specialised
 	std::mutex lock;
 };
 
@@ -352,7 +207,17 @@ static int batch_alloc(QPBatch *B)
 	B->smem_limit = (size_t)prop.sharedMemPerBlockOptin;
 	if (slice > B->smem_limit) return fail(QPB_E_PATTERN, "pattern does not fit in shared memory", cudaSuccess);
 	B->max_warps = (int)std::min<size_t>(MAX_WARPS_PER_CTA, B->smem_limit / slice);
-	CUDA_TRY(cudaFuncSetAttribute(qp_solve_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
+	CUDA_TRY(cudaFuncSetAttribute(qp_solve_warp_kernel<InterpretedWaves, MAX_WARPS_PER_CTA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
+	if (B->sprog.ok && !getenv("QPB_WARP_INTERPRET")) {
+		const GeneratedWarpKernel *g = find_generated_warp_kernel(stream_program_key(B->sprog));
+		if (g) {
+			B->gen_warp = g;
+			B->gen_warps = (int)std::min<size_t>(GEN_WARPS_PER_CTA, B->smem_limit / ((size_t)g->lay.total * sizeof(double)));
+			if (getenv("QPB_WARP_WARPS")) B->gen_warps = std::max(1, std::min(B->gen_warps, atoi(getenv("QPB_WARP_WARPS"))));
+			CUDA_TRY(cudaFuncSetAttribute(g->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
+			CUDA_TRY(cudaFuncSetAttribute(g->kernel_free, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
+		}
+	}
 	CUDA_TRY(cudaFuncSetAttribute(ldl_numeric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
 	CUDA_TRY(cudaFuncSetAttribute(ldl_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
 
@@ -430,13 +295,19 @@ static int batch_alloc_staging(QPBatch *B)
 static int launch_latency(QPBatch *B, const BatchIO &io, const SolveParams &prm, long count, int *counter, cudaStream_t st)
 {
 	// one persistent CTA per SM; small batches spread over the SMs with fewer warps per CTA
+	const int most = B->gen_warp ? B->gen_warps : B->max_warps;
 	long warps = (count + B->sm_count - 1) / B->sm_count;
-	if (warps > B->max_warps) warps = B->max_warps;
+	if (warps > most) warps = most;
 	if (warps < 1) warps = 1;
 	long grid = (count + warps - 1) / warps;
 	if (grid > B->sm_count) grid = B->sm_count;
-	const size_t smem = (size_t)warps * B->program.lay.total * sizeof(double);
-	qp_solve_cta_kernel<<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->d_plan, B->pview, B->program.lay, io, prm, counter);
+	const SliceLayout &lay = B->gen_warp ? B->gen_warp->lay : B->program.lay;
+	const size_t smem = (size_t)warps * lay.total * sizeof(double);
+	if (B->gen_warp) {
+		const int *plan = B->d_plan;
+		void *args[] = {&plan, &B->pview, const_cast<SliceLayout *>(&lay), const_cast<BatchIO *>(&io), const_cast<SolveParams *>(&prm), &counter};
+		CUDA_TRY(cudaLaunchKernel(getenv("QPB_WARP_FREE") && !io.server_done ? B->gen_warp->kernel_free : B->gen_warp->kernel, dim3((unsigned)grid), dim3((unsigned)warps * 32), args, smem, st));
+	} else qp_solve_warp_kernel<InterpretedWaves, MAX_WARPS_PER_CTA, true><<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->d_plan, B->pview, B->program.lay, io, prm, counter);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }
@@ -505,7 +376,8 @@ static int launch_stream(QPBatch *B, BatchIO io, SolveParams prm, cudaStream_t s
 			second = B->aux_stream;
 			CUDA_TRY(cudaStreamWaitEvent(second, B->ev_go2, 0));
 		}
-		const int rc = launch_latency(B, io, prm, server ? (long)B->max_warps : (long)B->sm_count * B->max_warps, second_counter, second);
+		const long lat_warps = B->gen_warp ? B->gen_warps : B->max_warps;
+		const int rc = launch_latency(B, io, prm, server ? lat_warps : (long)B->sm_count * lat_warps, second_counter, second);
 		if (rc) return rc;
 		if (server) {
 			CUDA_TRY(cudaEventRecord(B->ev_server, second));
@@ -535,7 +407,7 @@ static int launch_fused(QPBatch *B, BatchIO io, const settings *opts, cudaStream
 	if (!(B->d_workspace && io.count >= B->stream_min)) io.ready = nullptr; // only the throughput kernel waits for rows
 	CUDA_TRY(cudaMemsetAsync(B->d_counter, 0, sizeof(int), st));
 	if (B->d_workspace && io.count >= B->stream_min) return launch_stream(B, io, prm, st);
-	B->last_kernel = 0;
+	B->last_kernel = B->gen_warp ? 3 : 0;
 	B->last_launches = 1;
 	return launch_latency(B, io, prm, io.count, B->d_counter, st);
 }

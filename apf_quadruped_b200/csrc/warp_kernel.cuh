@@ -1,0 +1,240 @@
+// Warp-per-QP kernel of the batched interior-point solver (sm_100a, FP64): ONE WARP PER QP, the QP's whole
+// working set -- value row, factor L, pivots, iterate, residuals (SliceLayout, program.h) -- resident in the
+// warp's slice of SHARED memory from the coalesced load of its value row to the store of its solution.
+//
+// Launch shape: one persistent CTA per SM, as many warps as slices fit.  The warps of a CTA walk the
+// interior-point iteration in lock step -- [residuals + stop test | factor | solve | step length, sigma |
+// solve | update] -- so that they fetch the same code / instruction words at the same time.  A warp whose QP
+// has left the loop stores it and pulls the next QP index from an atomic counter at the top of the cycle; the
+// new QP's initial point (kkt_initialize) is just another factor + solve of the same cycle, so iteration
+// counts that differ from QP to QP cost no idle cycles.
+//
+// The kernel is a template over where LDL_numeric and the triangular solves come from:
+//   InterpretedWaves   the list-scheduled wave schedules of program.cpp, interpreted (any pattern);
+//   a GENERATED program (apf_quadruped_b200/codegen_warp.py): straight-line warp code for one pattern,
+//                      lane = row of L, L(j,i) read once per column step as a shared-memory broadcast.
+// Reference: QP_SOLVE qpSWIFT.c:473-644; the elementwise steps are kernels.cuh's.
+#pragma once
+
+#include "kernels.cuh"
+#include "warp_ipm.cuh"
+
+namespace qpb {
+
+struct ProgramView
+{
+	const uint2 *words;
+	int f_first, f_waves, f_width, s_first, s_waves, s_width;
+};
+
+enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_PRED = 2, MODE_CENT = 3 };
+static const int MAX_WARPS_PER_CTA = 16; // interpreted schedules: 128 registers per thread
+static const int GEN_WARPS_PER_CTA = 8;  // generated programs keep a row's work vector in registers: 255 per thread
+
+struct GeneratedWarpKernel
+{
+	unsigned long long key; // stream_program_key of the pattern the code was generated for
+	const void *kernel;     // qp_solve_warp_kernel<PROG, GEN_WARPS_PER_CTA, true>
+	const void *kernel_free; // ... <PROG, GEN_WARPS_PER_CTA, false>: the warps of a CTA never wait for one another
+	const char *name;
+	SliceLayout lay;        // the layout the addresses in the code assume (scratch cut down to what the code uses)
+};
+
+void register_generated_warp_kernel(unsigned long long key, const void *kernel, const void *kernel_free, const char *name, const SliceLayout &lay);
+const GeneratedWarpKernel *find_generated_warp_kernel(unsigned long long key);
+
+#ifdef __CUDACC__
+
+// One table-driven chain per lane (generated programs): acc -= S[ta[64 t]] * S[tb[64 t]], t ascending; ta / tb
+// point at the lane's column of 16-bit byte offsets, a step's rows of 32 lie 64 entries apart.
+__device__ __forceinline__ double lane_chain(double acc, const unsigned sb, const unsigned short *__restrict__ ta, const unsigned short *__restrict__ tb, const int steps)
+{
+	int t = 0;
+	for (; t + 4 <= steps; t += 4) {
+		unsigned oa[4], ob[4];
+		double va[4], vb[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) { oa[u] = __ldg(ta + 64 * (t + u)); ob[u] = __ldg(tb + 64 * (t + u)); }
+#pragma unroll
+		for (int u = 0; u < 4; ++u) { va[u] = lds64(sb + oa[u]); vb[u] = lds64(sb + ob[u]); }
+#pragma unroll
+		for (int u = 0; u < 4; ++u) acc = acc - va[u] * vb[u];
+	}
+	for (; t < steps; ++t) acc = acc - lds64(sb + __ldg(ta + 64 * t)) * lds64(sb + __ldg(tb + 64 * t));
+	return acc;
+}
+
+struct InterpretedWaves
+{
+	static constexpr bool own_residuals = false;
+	static constexpr bool realign = true;
+	static __device__ __forceinline__ void resid(const unsigned) {}
+	static __device__ __forceinline__ void factor(const ProgramView &pg, const unsigned sb, unsigned) { run_segment(pg.words, pg.f_first, pg.f_waves, pg.f_width, sb); }
+	static __device__ __forceinline__ void solve(const ProgramView &pg, const unsigned sb, unsigned) { run_segment(pg.words, pg.s_first, pg.s_waves, pg.s_width, sb); }
+};
+
+template <class PROG, int MAXW, bool CTA_SYNC>
+__global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *__restrict__ plan, ProgramView pg, SliceLayout lay, BatchIO io, SolveParams prm, int *__restrict__ counter)
+{
+	extern __shared__ __align__(16) double smem[];
+	const PlanView pv = view_of(plan);
+	const int lane = lane_id(), warp = threadIdx.x >> 5;
+	double *S = smem + (size_t)warp * lay.total;
+	const unsigned sb = (unsigned)__cvta_generic_to_shared(S);
+	WarpState w = carve(S, lay);
+	if (lane == 0) { S[lay.zero] = 0.0; S[lay.zero + 1] = -0.0; }
+	__syncwarp();
+	const int n = pv.n, m = pv.m, p = pv.p;
+	const double thr = prm.reltol / sqrt(3.0);
+
+	int q = 0, iters = 0;
+	bool active = false; // a QP is between its initial point and its exit
+	double sigma = 0.0, mu = 0.0, ap = 0.0, ad = 0.0;
+	Scalars sc;
+	sc.n_rx = sc.n_ry = sc.n_rz = sc.n_mu = sc.fval = 0.0;
+
+	for (;;) {
+		int mode = MODE_IDLE;
+		if (active) { // top of QP_SOLVE's loop (qpSWIFT.c:502-534)
+			int flag = -1;
+			double mu_next = mu; // (mu is updated after the stop test, qpSWIFT.c:538: a QP that leaves keeps the last one)
+			if (iters >= prm.maxit) flag = 2; // QP_MAXIT (qpSWIFT.c:604-607)
+			else {
+				if (PROG::own_residuals) PROG::resid(sb);
+				else ipm_residual_products(pv, w.V, w.c, w.h, w.b, w.x, w.y, w.z, w.s, w.r, S + lay.T /* scratch: -(P x) */);
+				const IterSums sums = ipm_sums(n, m, p, sb, lay, lay.T);
+				sc = sums.sc;
+				mu_next = sums.mu;
+				if (sc.n_rx < thr && sc.n_rz < thr && (p == 0 || sc.n_ry < thr) && sc.n_mu < prm.abstol) flag = 0;
+			}
+			if (flag >= 0) {
+				const size_t qi = (size_t)q;
+				warp_copy_out(io.x ? io.x + qi * n : nullptr, w.x, n);
+				if (p) warp_copy_out(io.y ? io.y + qi * p : nullptr, w.y, p);
+				warp_copy_out(io.z ? io.z + qi * m : nullptr, w.z, m);
+				warp_copy_out(io.s ? io.s + qi * m : nullptr, w.s, m);
+				if (lane == 0) {
+					if (io.flag) io.flag[q] = flag;
+					if (io.iters) io.iters[q] = iters;
+					if (io.fval) io.fval[q] = sc.fval;
+					if (io.stat) {
+						double *st = io.stat + qi * 8;
+						st[0] = sc.n_rx; st[1] = sc.n_ry; st[2] = sc.n_rz; st[3] = sc.n_mu;
+						st[4] = ap; st[5] = ad; st[6] = sigma; st[7] = mu;
+					}
+				}
+				__syncwarp();
+				active = false;
+			} else {
+				__syncwarp();
+				mu = mu_next;
+				const bool centering = !(sigma > prm.sigma_d); // predictor: ds = -lambda^2 (qpSWIFT.c:540-552); else the centering step only (572-579)
+				if (centering) sigma = prm.sigma_d;
+				mode = centering ? MODE_CENT : MODE_PRED;
+				ipm_begin_step(n, m, p, w, centering, sigma * mu);
+			}
+		}
+		bool may_leave = true;
+		if (!active) { // next QP: load its value row, set up kkt_initialize's system
+			if (lane == 0) {
+				if (!io.server_done) {
+					q = atomicAdd(counter, 1);
+					const int limit = io.count_ptr ? *io.count_ptr : io.count;
+					q = q < limit ? (io.index ? io.index[q] : q) : -1; // the QP behind the ticket (| iterations << 24)
+				} else { // server: the list grows while the throughput kernel runs; one attempt per turn, never a wait
+					const int done = *reinterpret_cast<const volatile int *>(io.server_done); // (read before the count)
+					__threadfence();
+					const int limit = *reinterpret_cast<const volatile int *>(io.count_ptr);
+					const int cur = *reinterpret_cast<volatile int *>(counter);
+					q = -1;
+					if (cur < limit) {
+						may_leave = false;
+						const int listed = reinterpret_cast<const volatile int *>(io.index)[cur];
+						if (listed >= 0 && atomicCAS(counter, cur, cur + 1) == cur) q = listed;
+						__threadfence(); // the entry before what it points at
+					} else if (!done) may_leave = false;
+				}
+			}
+			q = __shfl_sync(0xffffffffu, q, 0);
+			if (q >= 0) {
+				// list entries carry the iteration count in the high byte only while QP indices fit 24 bits (stream.cuh)
+				const bool packed = io.index && io.count < (1 << 24);
+				const int resume_at = packed ? (q >> 24) : 0; // > 0: a straggler's iterate is waiting in the output arrays
+				if (packed) q &= (1 << 24) - 1;
+				const size_t qi = (size_t)q;
+				warp_copy_in(w.V, io.Ppr + qi * pv.offA, pv.offA);
+				if (p) warp_copy_in(w.V + pv.offA, io.Apr + qi * (pv.offG - pv.offA), pv.offG - pv.offA);
+				warp_copy_in(w.V + pv.offG, io.Gpr + qi * (pv.nV - pv.offG), pv.nV - pv.offG);
+				warp_copy_in(w.c, io.c + qi * n, n);
+				warp_copy_in(w.h, io.h + qi * m, m);
+				if (p) warp_copy_in(w.b, io.b + qi * p, p);
+				__syncwarp();
+				if (resume_at > 0 && io.spill_sigma) {
+					// the state of QP_SOLVE's loop between two iterations is (x, y, z, s, sigma, IterationCount);
+					// everything else is recomputed at the top of the next one (qpSWIFT.c:502-552)
+					warp_copy_in(w.x, io.x + qi * n, n);
+					if (p) warp_copy_in(w.y, io.y + qi * p, p);
+					warp_copy_in(w.z, io.z + qi * m, m);
+					warp_copy_in(w.s, io.s + qi * m, m);
+					__syncwarp();
+					iters = resume_at;
+					sigma = io.spill_sigma[q];
+					mu = ap = ad = 0.0;
+					active = true;
+					may_leave = false;
+				} else {
+					ipm_init_rhs(pv, w);
+					iters = 0;
+					sigma = prm.sigma0;
+					mu = ap = ad = 0.0;
+					mode = MODE_INIT;
+				}
+			}
+		}
+		// how many threads of the CTA run factor + solve now: they meet at barriers inside the generated code
+		const unsigned busy = CTA_SYNC ? (unsigned)__syncthreads_count(mode != MODE_IDLE) : (mode != MODE_IDLE ? 32u : 0u);
+		if (!busy) {
+			if (!(CTA_SYNC ? __syncthreads_or(!may_leave) : (int)!may_leave)) break;
+			__nanosleep(2000); // a server with nothing listed yet
+			continue;
+		}
+
+		if (mode != MODE_IDLE) {
+			PROG::factor(pg, sb, busy);
+			PROG::solve(pg, sb, busy);
+		}
+		if (mode == MODE_INIT) {
+			ipm_init_point(pv, w);
+			active = true;
+		} else if (mode == MODE_PRED) { // affine step length, sigma, corrector right-hand side (qpSWIFT.c:564-570)
+			ipm_recover_and_steplength(n, m, p, w, ap, ad);
+			sigma = ipm_sigma_and_corrector(n, m, p, w, sb, lay.T, ap, ad, prm.sigma_d, mu);
+		}
+		// (re-aligns the warps where the program wants that: interpreted schedules stream their words together)
+		const unsigned again = CTA_SYNC && PROG::realign ? (unsigned)__syncthreads_count(mode == MODE_PRED) : 32u;
+		if (mode == MODE_PRED) PROG::solve(pg, sb, again);
+		if (mode == MODE_PRED || mode == MODE_CENT) { // step, damping, update (qpSWIFT.c:584-596)
+			ipm_recover_and_steplength(n, m, p, w, ap, ad);
+			ipm_update(n, m, p, w, ap, ad);
+			++iters;
+		}
+	}
+}
+
+#define QPB_REGISTER_GENERATED_WARP(tag, key, layout, PROG)                                                                          \
+	template __global__ void qp_solve_warp_kernel<PROG, GEN_WARPS_PER_CTA, true>(const int *__restrict__, ProgramView, SliceLayout, BatchIO, SolveParams, int *__restrict__);  \
+	template __global__ void qp_solve_warp_kernel<PROG, GEN_WARPS_PER_CTA, false>(const int *__restrict__, ProgramView, SliceLayout, BatchIO, SolveParams, int *__restrict__); \
+	namespace {                                                                                                                           \
+	struct RegisterWarp_##tag                                                                                                             \
+	{                                                                                                                                     \
+		RegisterWarp_##tag()                                                                                                              \
+		{                                                                                                                                 \
+			register_generated_warp_kernel(key, reinterpret_cast<const void *>(&qp_solve_warp_kernel<PROG, GEN_WARPS_PER_CTA, true>),     \
+			                               reinterpret_cast<const void *>(&qp_solve_warp_kernel<PROG, GEN_WARPS_PER_CTA, false>), #tag, layout); \
+		}                                                                                                                                 \
+	} register_warp_##tag;                                                                                                                \
+	}
+
+#endif // __CUDACC__
+
+} // namespace qpb

@@ -358,12 +358,12 @@ class BatchSolver:
 
     @property
     def last_kernel(self) -> str:
-        return {0: "warp", 1: "stream", 2: "stream"}.get(int(lib().QPB_BATCH_LAST_KERNEL(self.handle)), "?")
+        return {0: "warp", 1: "stream", 2: "stream", 3: "warp"}.get(int(lib().QPB_BATCH_LAST_KERNEL(self.handle)), "?")
 
     @property
     def last_kernel_generated(self) -> bool:
-        """The throughput kernel that ran was the pattern-specialised one (codegen.py), not the interpreter."""
-        return int(lib().QPB_BATCH_LAST_KERNEL(self.handle)) == 2
+        """The kernel that ran was a pattern-specialised one (codegen.py / codegen_warp.py), not an interpreter."""
+        return int(lib().QPB_BATCH_LAST_KERNEL(self.handle)) in (2, 3)
 
     @property
     def last_launches(self) -> int:

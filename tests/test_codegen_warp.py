@@ -1,0 +1,129 @@
+"""Host check of the pattern-specialised warp-per-QP programs (apf_quadruped_b200/codegen_warp.py) -- no GPU.
+
+The generator's IR is executed by its emulator (32 lanes in lock step, with the cross-lane hazard check: a
+double written by one lane and read by another needs a __syncwarp in between) and compared bit for bit
+with the reference's LDL_numeric, LDL solves (ldl.c:253-326, 495-597, through oracle.reference) and with a
+plain restatement of computeresiduals' products (Auxilary.c:753-785)."""
+import numpy as np
+import pytest
+
+from apf_quadruped_b200 import codegen_warp as W
+from apf_quadruped_b200 import dogbot
+
+
+def make_slice(lay, batch, i):
+    pat = batch.pattern
+    S = np.full(lay["total"], np.nan)
+    S[lay["zero"]] = 0.0
+    S[lay["zero"] + 1] = -0.0
+    vals = np.concatenate([batch.Ppr[i], batch.Apr[i], batch.Gpr[i]])
+    S[lay["V"]:lay["V"] + vals.size] = vals
+    S[lay["c"]:lay["c"] + pat.n] = batch.c[i]
+    S[lay["h"]:lay["h"] + pat.m] = batch.h[i]
+    S[lay["b"]:lay["b"] + pat.p] = batch.b[i]
+    S[lay["zd"]:lay["zd"] + pat.m] = -1.0
+    return S
+
+
+def residual_products(pat, Ppr, Apr, Gpr, c, h, b, x, y, z, s):
+    """Auxilary.c:753-785: column scatter for P x, A x, G x; column gather for G'z, A'y."""
+    def scatter(jc, ir, pr, xin, out):
+        for col in range(len(jc) - 1):
+            for q in range(jc[col], jc[col + 1]):
+                out[ir[q]] -= xin[col] * pr[q]
+
+    def gather(jc, ir, pr, xin, out):
+        for col in range(len(jc) - 1):
+            for q in range(jc[col], jc[col + 1]):
+                out[col] -= pr[q] * xin[ir[q]]
+
+    rx = np.zeros(pat.n)
+    scatter(pat.Pjc, pat.Pir, Ppr, x, rx)
+    px = rx.copy()
+    gather(pat.Gjc, pat.Gir, Gpr, z, rx)
+    if pat.p:
+        gather(pat.Ajc, pat.Air, Apr, y, rx)
+    rx += c * (-1.0)
+    ry = np.zeros(pat.p)
+    if pat.p:
+        scatter(pat.Ajc, pat.Air, Apr, x, ry)
+        ry += b * 1.0
+    rz = np.zeros(pat.m)
+    scatter(pat.Gjc, pat.Gir, Gpr, x, rz)
+    rz += h - s
+    return np.concatenate([rx, ry, rz]), px
+
+
+@pytest.mark.parametrize("kind", ["trot", "stance", "crawl"])
+def test_generated_warp_programs_reproduce_the_reference(qps, oracle, kind):
+    batch = dogbot.generate(kind, 2, start=321)
+    pat = batch.pattern
+    plan = qps.Plan(pat)
+    st = W.Structure(plan)
+    fac, sol, res = W.gen_factor(st), W.gen_solve(st), W.gen_resid(st)
+    lay = st.lay
+    assert all(len(rows) <= 32 for rows in fac.passes) and sorted(k for rows in fac.passes for k in rows) == st.R
+    N, lnz, n, m, p = plan.info("N"), plan.info("lnz"), pat.n, pat.m, pat.p
+    for i in range(batch.count):
+        S = make_slice(lay, batch, i)
+        ref = oracle.solve_sparse(pat, batch.Ppr[i], batch.Apr[i], batch.Gpr[i], batch.c[i], batch.h[i], batch.b[i],
+                                  maxit=0, want_factor=True)
+        W.Emulator(fac, S).run()
+        assert np.array_equal(S[lay["Lx"]:lay["Lx"] + lnz], ref.init["Lx"])
+        assert np.array_equal(S[lay["D"]:lay["D"] + N], ref.init["D"])  # regularised pivots (ldl.c:319-320)
+        S[lay["rhs"]:lay["rhs"] + N] = np.concatenate([-batch.c[i], batch.b[i], batch.h[i]])
+        W.Emulator(sol, S).run()
+        x = S[lay["rhs"]:lay["rhs"] + N]
+        assert np.array_equal(x[:n], ref.init["x"]) and np.array_equal(x[n:n + p], ref.init["y"])
+        assert not np.isnan(x).any()
+        rng = np.random.default_rng(i)
+        xv, yv, zv, sv = rng.standard_normal(n), rng.standard_normal(p), rng.random(m) + 0.1, rng.random(m) + 0.1
+        for name, v in (("x", xv), ("y", yv), ("z", zv), ("s", sv)):
+            S[lay[name]:lay[name] + v.size] = v
+        W.Emulator(res, S).run()
+        r, px = residual_products(pat, batch.Ppr[i], batch.Apr[i], batch.Gpr[i], batch.c[i], batch.h[i], batch.b[i], xv, yv, zv, sv)
+        assert np.array_equal(S[lay["r"]:lay["r"] + N], r)
+        assert np.array_equal(S[lay["T"]:lay["T"] + n], px)
+
+
+def test_zero_right_hand_side_takes_the_exact_quotient(qps, oracle):
+    """LDL_dsolve on exact zeros (the trot QP's b is all zero): x / D must stay +-0 with the reference's sign."""
+    batch = dogbot.generate("trot", 1, start=5)
+    plan = qps.Plan(batch.pattern)
+    st = W.Structure(plan)
+    fac, sol = W.gen_factor(st), W.gen_solve(st)
+    lay, N = st.lay, plan.info("N")
+    S = make_slice(lay, batch, 0)
+    W.Emulator(fac, S).run()
+    rhs = np.zeros(N)
+    rhs[::3] = -0.0
+    S[lay["rhs"]:lay["rhs"] + N] = rhs
+    W.Emulator(sol, S).run()
+    out = S[lay["rhs"]:lay["rhs"] + N]
+    assert np.all(out == 0.0)
+
+
+def test_emulator_flags_missing_syncs():
+    ir = W.IR("t")
+    v = ir.lds(None, 0, 1)
+    ir.emit("sync")
+    ir.emit("sts", None, 8, 1, v, None)   # lane l writes double l + 1 ...
+    ir.lds(None, 0, 1)                    # ... which lane l + 1 reads without a sync
+    with pytest.raises(AssertionError):
+        W.Emulator(ir, np.zeros(64)).run()
+    ir2 = W.IR("t")
+    v = ir2.lds(None, 0, 1)
+    ir2.emit("sync")                      # (the store below overwrites what the neighbour has just read)
+    ir2.emit("sts", None, 8, 1, v, None)
+    ir2.emit("sync")
+    ir2.lds(None, 0, 1)
+    W.Emulator(ir2, np.zeros(64)).run()
+
+
+def test_layout_fits_more_warps_than_the_interpreted_one(qps):
+    for kind in ("trot", "stance", "crawl"):
+        plan = qps.Plan(dogbot.generate(kind, 1).pattern)
+        st = W.Structure(plan)
+        full = plan.layout()
+        assert st.lay["total"] < full["total"] and st.lay["tsize"] >= 2 * plan.pattern.m
+        assert all(st.lay[k] % 2 == 0 for k in W.LAYOUT_FIELDS if k not in ("total", "tsize"))
