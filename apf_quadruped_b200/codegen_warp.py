@@ -17,6 +17,9 @@ that every number is still produced by the reference's own sequence of IEEE-754 
   starts as 0 + v).  Columns that are leaves of the elimination tree (the inequality rows the ordering
   eliminates first) receive no updates: their pivots and their entries L(k,i) = K(i,k)/D[i] are computed
   beforehand, 32 at a time.
+  "Y[i] += value" from Y[i] == 0 (ldl.c:284) is v + 0.0, i.e. v except that -0.0 becomes +0.0: the kernel
+  normalises the matrix values that way once, when it loads them (the residual products cannot tell the
+  difference: their accumulators are never -0.0 either).
 * LDL_lsolve / dsolve / ltsolve (ldl.c:495-557).  Forward: lane = row r, w_r -= L(r,j)*w_j in ascending j
   (leaf columns: every lane walks its own row through per-lane tables; other columns: w_j comes by shuffle).
   Backward: the sum of a column is sequential by definition; its products are formed 32 at a time, the
@@ -425,7 +428,6 @@ def gen_factor(st: Structure, passes=None) -> IR:
     for w in range(0, len(st.leaf), NLANE):
         chunk = st.leaf[w:w + NLANE]
         v = ir.gather([st.kdiag[i] for i in chunk], ZERO)
-        v = ir.op("add0", v)
         v = ir.op("regu", v)
         ir.scatter([st.D(i) for i in chunk], v)
     ir.emit("sync")
@@ -436,7 +438,6 @@ def gen_factor(st: Structure, passes=None) -> IR:
         for q, k, i in chunk:
             assert st.kinit[(k, i)] is not None, "entry of a leaf column without a KKT entry"
         y = ir.gather([st.kinit[(k, i)] for q, k, i in chunk], ZERO)
-        y = ir.op("add0", y)
         dv = ir.gather([st.D(i) for q, k, i in chunk], st.D(chunk[0][2]))
         l = ir.op("div", y, dv)
         ir.scatter([st.Lx(q) for q, k, i in chunk], l)
@@ -452,7 +453,6 @@ def gen_factor(st: Structure, passes=None) -> IR:
             raise ValueError("the rows' Pattern orders have no common extension")
         inpat = {k: set(st.pat[k]) for k in rows}
         d = ir.gather([st.kdiag[k] for k in rows], ZERO)
-        d = ir.op("add0", d)
         Y, published = {}, set()
 
         def work(j):
@@ -462,13 +462,13 @@ def gen_factor(st: Structure, passes=None) -> IR:
                     v = ir.d()
                     ir.emit("const", v, 0.0)
                 else:
-                    v = ir.op("add0", ir.gather(offs, ZERO))
+                    v = ir.gather(offs, ZERO)
                 Y[j] = v
             return Y[j]
 
         for i in order:
             if st.is_leaf[i]:
-                y = ir.op("add0", ir.gather([st.kinit[(k, i)] if i in inpat[k] else None for k in rows], ZERO))
+                y = ir.gather([st.kinit[(k, i)] if i in inpat[k] else None for k in rows], ZERO)
                 l = ir.gather([st.Lx(st.colpos[(k, i)]) if i in inpat[k] else None for k in rows], ZERO)
                 d = ir.op("msub", d, l, y)  # D[k] -= l*y  (ldl.c:306)
             else:
@@ -591,7 +591,31 @@ def gen_solve(st: Structure, passes=None) -> IR:
         ir.scatter([X(j) for j in js], v)
     ir.emit("sync")
     # ---- LDL_ltsolve: w[j] -= Lx[q]*w[Li[q]], q ascending, j descending (ldl.c:539-557) ------------------
-    for j in reversed(nonleaf):  # columns whose rows are accumulators of the sweep itself: strictly sequential
+    # The columns of the last pass (the dense tail of L): lane = column.  When w[r] becomes final it is broadcast by
+    # shuffle and every lane forms ITS product L(r,j) w[r] into a register named after r; the sum of column j then
+    # runs over registers, in ascending r as the reference does (it is computed by all lanes, kept by lane(j)).
+    last = passes[-1]
+    lane_last = {j: l for l, j in enumerate(last)}
+    acc = ir.gather([X(j) for j in last], ZERO)
+    ir.emit("sync")  # (every lane stores the final w[r] back over what its owner has just read)
+    prod = {}
+    for r in reversed(last):
+        ent = st.col(r)
+        assert all(rr in lane_last for rr, _ in ent)
+        if ent:
+            t = acc
+            for rr, _ in ent:
+                t = ir.op("sub", t, prod[rr])
+            mine = ir.p()
+            ir.emit("prange", mine, lane_last[r], lane_last[r])
+            acc = ir.op("sel", mine, t, acc)
+        xr = ir.op("shfl", acc, lane_last[r])
+        ir.emit("sts", None, X(r), 0, xr, None)
+        offs = [st.Lx(st.colpos[(r, j)]) if (r, j) in st.colpos else None for j in last]
+        if any(o is not None for o in offs):
+            prod[r] = ir.op("mul", ir.gather(offs, ZERO), xr)
+    ir.emit("sync")
+    for j in reversed([c for c in nonleaf if c not in lane_last]):  # earlier passes: products through shared memory
         ent = st.col(j)
         acc = ir.lds(None, X(j), 0)  # (read before the sync below: every lane stores the sum back over it)
         for r0 in range(0, len(ent), NLANE):

@@ -186,6 +186,9 @@ struct QPBatch
 	cudaStream_t aux_stream = nullptr;  // the stragglers' server (latency kernel next to the throughput kernel)
 	int *h_marks = nullptr;             // pinned: the "rows [0, mark) have arrived" values written after each chunk
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	double *d_trace = nullptr; // per-iteration trace of the warp-per-QP kernel (QPB_BATCH_ENABLE_TRACE), [capacity][trace_rows][8]
+	long trace_rows = 0;
+	bool trace_on = false;
 	double last_kernel_ms = 0.0;
 	long last_launches = 0;
 	int last_kernel = 0; // 0 warp-per-QP kernel (interpreted schedules), 1 throughput kernel (one QP per thread), 2 the same, pattern-specialised, 3 warp-per-QP kernel, pattern-specialised
@@ -250,7 +253,12 @@ static int batch_alloc(QPBatch *B)
 		for (int s = 0; s < SSEG_COUNT; ++s) { B->sview.first[s] = sp.seg[s].first; B->sview.groups[s] = sp.seg[s].groups; }
 		const long full = (long)B->sm_count * B->stream_warps;
 		B->stream_slots = std::min(full, (B->capacity + 31) / 32);
-		B->stream_min = getenv("QPB_STREAM_MIN") ? atol(getenv("QPB_STREAM_MIN")) : 2048;
+		// Which kernel takes a batch.  Without a pattern-specialised warp-per-QP kernel: the throughput kernel from
+		// 2048 QPs on.  With one (DogBot trot / stance / crawl): the warp-per-QP kernel keeps the factor in shared
+		// memory, has no tail (1,184 QPs in flight instead of 37,888) and no stragglers' hand-over, and matches the
+		// throughput kernel up to a few waves of its lanes; beyond three waves (113,664 QPs) the throughput kernel's
+		// tail no longer matters and it is the faster one.  QPB_STREAM_MIN overrides.
+		B->stream_min = getenv("QPB_STREAM_MIN") ? atol(getenv("QPB_STREAM_MIN")) : (B->gen_warp ? 3 * full * 32 : 2048);
 		// A pattern whose window leaves room for fewer than 4 warps per SM (e.g. the horizon-10 MPC QP:
 		// N = 600, one warp) is faster on the latency kernel; QPB_STREAM_MIN_WARPS overrides.
 		const long min_warps = getenv("QPB_STREAM_MIN_WARPS") ? atol(getenv("QPB_STREAM_MIN_WARPS")) : 4;
@@ -367,6 +375,7 @@ static int launch_stream(QPBatch *B, BatchIO io, SolveParams prm, cudaStream_t s
 		io.spill = nullptr;
 		io.spill_count = nullptr;
 		io.ready = nullptr;
+		io.trace = nullptr;
 		io.done_ctas = nullptr;
 		io.server_done = server ? all_done : nullptr;
 		io.all_done = nullptr;
@@ -499,8 +508,8 @@ QPBatch *QPB_BATCH_CREATE(const QPBPlan *plan, qp_real sigma_d, qp_int capacity,
 {
 	if (!plan || capacity < 1) { g_last_error = "QPB_BATCH_CREATE: bad argument"; return nullptr; }
 	if (!plan->plan.valid) { g_last_error = "QPB_BATCH_CREATE: unusable pattern (an inequality row is empty)"; return nullptr; }
-	QPBatch *B = new QPBatch;
 	if (!plan->program.ok) { g_last_error = "QPB_BATCH_CREATE: " + plan->program.error; return nullptr; }
+	QPBatch *B = new QPBatch;
 	B->plan = plan->plan;
 	B->program = plan->program;
 	B->sprog = plan->stream;
@@ -531,6 +540,7 @@ void QP_CLEANUP_BATCH(QPBatch *B)
 	for (int k = 0; k < 3; ++k) { cudaFree(B->d_dense_map[k]); cudaFree(B->d_dense[k]); }
 	cudaFree(B->d_violation);
 	cudaFree(B->d_workspace);
+	cudaFree(B->d_trace);
 	cudaFree(B->d_spill);
 	cudaFree(B->d_counter);
 	for (int i = 0; i < 6; ++i) cudaFree(B->d_in[i]);
@@ -553,7 +563,8 @@ void QP_CLEANUP_BATCH(QPBatch *B)
 
 qp_int QP_SOLVE_BATCH_DEVICE(QPBatch *B, qp_int count, const settings *opts, const qp_real *dPpr, const qp_real *dApr, const qp_real *dGpr, const qp_real *dc, const qp_real *dh, const qp_real *db, qp_real *dx, qp_real *dy, qp_real *dz, qp_real *ds, int *dflag, int *diters, qp_real *dfval, qp_real *dstat, void *stream)
 {
-	if (!B || !opts || count < 0 || !dPpr || !dGpr || !dc || !dh || (B->plan.p && (!dApr || !db))) return fail(QPB_E_ARG, "QP_SOLVE_BATCH_DEVICE: bad argument", cudaSuccess);
+	// (the spill list and sigma array of the throughput kernel are sized by the capacity)
+	if (!B || !opts || count < 0 || count > B->capacity || !dPpr || !dGpr || !dc || !dh || (B->plan.p && (!dApr || !db))) return fail(QPB_E_ARG, "QP_SOLVE_BATCH_DEVICE: bad argument (null pointer, count > capacity)", cudaSuccess);
 	if (count == 0) return 0;
 	CUDA_TRY(cudaSetDevice(B->device));
 	BatchIO io;
@@ -561,6 +572,7 @@ qp_int QP_SOLVE_BATCH_DEVICE(QPBatch *B, qp_int count, const settings *opts, con
 	io.x = dx; io.y = dy; io.z = dz; io.s = ds; io.flag = dflag; io.iters = diters; io.fval = dfval; io.stat = dstat;
 	io.count = (int)count;
 	io.ready = nullptr;
+	io.trace = nullptr;
 	return launch_fused(B, io, opts, (cudaStream_t)stream);
 }
 
@@ -591,6 +603,18 @@ static qp_int qp_solve_batch_host(QPBatch *B, qp_int count, const settings *opts
 	io.x = B->d_x; io.y = B->d_y; io.z = B->d_z; io.s = B->d_s; io.flag = B->d_flag; io.iters = B->d_iters; io.fval = B->d_fval; io.stat = B->d_stat;
 	io.count = (int)count;
 	io.ready = nullptr;
+	io.trace = nullptr;
+	if (B->trace_on) { // verbose single solves (QP_SOLVE): per-iteration lines and the time in LDL_numeric
+		const long rows = (long)opts->maxit + 2;
+		if (rows > B->trace_rows) {
+			cudaFree(B->d_trace);
+			B->d_trace = nullptr;
+			CUDA_TRY(cudaMalloc(&B->d_trace, (size_t)B->capacity * rows * 8 * sizeof(double)));
+			B->trace_rows = rows;
+		}
+		CUDA_TRY(cudaMemsetAsync(B->d_trace, 0, (size_t)B->capacity * B->trace_rows * 8 * sizeof(double), st));
+		io.trace = B->d_trace;
+	}
 	// Results straight into the caller's buffers where those are page-locked (and therefore mapped into the
 	// device's address space): the throughput kernel writes a finished QP's rows 256 bytes at a time over the
 	// bus while the others are still being solved, instead of one copy of everything after the kernel.
@@ -719,6 +743,24 @@ qp_int QPB_BATCH_SET_SIGMA_D(QPBatch *B, qp_real sigma_d)
 	return 0;
 }
 
+// Per-iteration trace of the warp-per-QP kernel for the next host-pointer solves (small batches only: the throughput
+// kernel does not trace).  Layout per QP: (maxit + 2) rows of 8 doubles, see BatchIO::trace (kernels.cuh).
+qp_int QPB_BATCH_ENABLE_TRACE(QPBatch *B, int on)
+{
+	if (!B) return fail(QPB_E_ARG, "QPB_BATCH_ENABLE_TRACE: null batch", cudaSuccess);
+	if (on && B->capacity >= B->stream_min && B->d_workspace) return fail(QPB_E_ARG, "QPB_BATCH_ENABLE_TRACE: batches of this capacity run the throughput kernel, which keeps no trace", cudaSuccess);
+	B->trace_on = on != 0;
+	return 0;
+}
+
+qp_int QPB_BATCH_READ_TRACE(QPBatch *B, qp_int count, qp_int maxit, qp_real *trace)
+{
+	if (!B || !trace || !B->d_trace || count < 0 || count > B->capacity || maxit + 2 != B->trace_rows) return fail(QPB_E_ARG, "QPB_BATCH_READ_TRACE: no trace of that shape", cudaSuccess);
+	CUDA_TRY(cudaSetDevice(B->device));
+	CUDA_TRY(cudaMemcpy(trace, B->d_trace, (size_t)count * B->trace_rows * 8 * sizeof(double), cudaMemcpyDeviceToHost));
+	return 0;
+}
+
 double QPB_BATCH_LAST_KERNEL_MS(const QPBatch *B) { return B ? B->last_kernel_ms : 0.0; }
 qp_int QPB_BATCH_LAST_LAUNCHES(const QPBatch *B) { return B ? B->last_launches : 0; }
 int QPB_BATCH_LAST_KERNEL(const QPBatch *B) { return B ? B->last_kernel : -1; }
@@ -728,6 +770,7 @@ qp_int QPB_GENERATED_KERNELS(unsigned long long *keys, int capacity) { return li
 qp_int QPB_BATCH_READ_STATS(QPBatch *B, qp_int count, qp_real *fval, qp_real *stat)
 {
 	if (!B || !B->d_fval) return fail(QPB_E_ARG, "QPB_BATCH_READ_STATS: nothing solved yet", cudaSuccess);
+	if (count < 0 || count > B->capacity) return fail(QPB_E_ARG, "QPB_BATCH_READ_STATS: count > capacity", cudaSuccess);
 	CUDA_TRY(cudaSetDevice(B->device));
 	if (fval) CUDA_TRY(cudaMemcpy(fval, B->d_fval, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost));
 	if (stat) CUDA_TRY(cudaMemcpy(stat, B->d_stat, (size_t)count * 8 * sizeof(double), cudaMemcpyDeviceToHost));

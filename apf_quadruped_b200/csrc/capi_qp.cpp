@@ -8,9 +8,14 @@
 //   * the initial point (kkt_initialize) is computed by the solve kernel, not at setup;
 //   * QP_SOLVE always restarts from that initial point (the reference's second call on the same
 //     QP is undefined: IterationCount is never reset, qpSWIFT.c:596);
-//   * plans are cached per sparsity pattern, so a controller that calls QP_SETUP_dense every
-//     tick (main.cpp:1649) pays for AMD + symbolic analysis once, and one that never calls
-//     QP_CLEANUP (the reference controller does not) leaks only its own QP struct;
+//   * plans are cached per sparsity pattern (at most PLAN_CACHE_SIZE of them, least recently used
+//     out first), so a controller that calls QP_SETUP_dense every tick (main.cpp:1649) pays for AMD +
+//     symbolic analysis once per pattern; a pattern change (an entry that becomes exactly 0.0) costs
+//     one analysis + program compilation + cudaMalloc, i.e. a latency spike of a few milliseconds;
+//   * what QP_SOLVE needs beyond the public structs hangs off the QP itself (a private tail behind
+//     its kkt struct): there is no table of live QPs, and a controller that never calls QP_CLEANUP
+//     (the reference controller does not) leaks exactly what it leaks with the reference -- its own
+//     QP -- and nothing inside the library grows;
 //   * without a usable CUDA device QP_SOLVE returns QP_FATAL; there is no CPU solver here.
 
 #include "capi_internal.h"
@@ -32,15 +37,36 @@ struct CachedPlan
 {
 	QPBPlan handle;
 	std::vector<long> key; // the exact pattern this plan was built for (collision check)
+	uint64_t hash = 0;
 	QPBatch *single = nullptr;
 	bool single_failed = false;
+	std::mutex solve_lock; // one QP_SOLVE at a time on the shared single-QP batch (sigma_d, solve, statistics)
+	unsigned long long last_use = 0;
 	~CachedPlan() { if (single) QP_CLEANUP_BATCH(single); }
 };
 
+const size_t PLAN_CACHE_SIZE = 16;
 std::mutex g_lock;
-std::unordered_map<uint64_t, std::vector<std::shared_ptr<CachedPlan>>> g_plans;
-struct Registered { std::shared_ptr<CachedPlan> plan; bool dense; };
-std::unordered_map<const QP *, Registered> g_live;
+std::vector<std::shared_ptr<CachedPlan>> g_plans; // bounded; a QP keeps its plan alive on its own
+unsigned long long g_clock = 0;
+
+// What QP_SOLVE needs to find again, allocated in one block with the public kkt struct (which comes first, so
+// that qp->kkt points at it): no global table of live QPs.
+struct KktBlock
+{
+	kkt pub;
+	uint64_t magic;
+	std::shared_ptr<CachedPlan> plan;
+	bool dense;
+};
+const uint64_t KKT_MAGIC = 0x51505342323030ull; // "QPSB200"
+
+KktBlock *block_of(const QP *qp)
+{
+	if (!qp || !qp->kkt) return nullptr;
+	KktBlock *b = reinterpret_cast<KktBlock *>(qp->kkt);
+	return b->magic == KKT_MAGIC ? b : nullptr;
+}
 
 template <class T>
 T *alloc(size_t count) { return (T *)malloc((count ? count : 1) * sizeof(T)); }
@@ -57,12 +83,20 @@ std::shared_ptr<CachedPlan> plan_for(qp_int n, qp_int m, qp_int p, const qp_int 
 	if (Permut) push(key, Permut, n + m + p);
 	const uint64_t h = qpb::fnv1a_words(key.data(), (long)key.size());
 	std::lock_guard<std::mutex> guard(g_lock);
-	for (auto &cand : g_plans[h])
-		if (cand->key == key) return cand;
+	for (auto &cand : g_plans)
+		if (cand->hash == h && cand->key == key) { cand->last_use = ++g_clock; return cand; }
 	auto made = std::make_shared<CachedPlan>();
 	qpb_build(made->handle, n, m, p, Pjc, Pir, p ? Ajc : nullptr, p ? Air : nullptr, Gjc, Gir, Permut);
 	made->key.swap(key);
-	g_plans[h].push_back(made);
+	made->hash = h;
+	made->last_use = ++g_clock;
+	if (g_plans.size() >= PLAN_CACHE_SIZE) { // least recently used out; QPs that still hold it keep it alive
+		size_t oldest = 0;
+		for (size_t i = 1; i < g_plans.size(); ++i)
+			if (g_plans[i]->last_use < g_plans[oldest]->last_use) oldest = i;
+		g_plans.erase(g_plans.begin() + (long)oldest);
+	}
+	g_plans.push_back(made);
 	return made;
 }
 
@@ -155,7 +189,12 @@ QP *setup_common(qp_int n, qp_int m, qp_int p, smat *P, smat *A, smat *G, qp_rea
 	auto cached = plan_for(n, m, p, P->jc, P->ir, A ? A->jc : nullptr, A ? A->ir : nullptr, G->jc, G->ir, Permut);
 	const Plan &pl = cached->handle.plan;
 
-	kkt *k = (kkt *)calloc(1, sizeof(kkt));
+	KktBlock *blk = new KktBlock();
+	memset(&blk->pub, 0, sizeof(kkt));
+	blk->magic = KKT_MAGIC;
+	blk->plan = cached;
+	blk->dense = dense;
+	kkt *k = &blk->pub;
 	qp->kkt = k;
 	k->kktmatrix = alloc<smat>(1);
 	k->kktmatrix->m = k->kktmatrix->n = N;
@@ -192,10 +231,6 @@ QP *setup_common(qp_int n, qp_int m, qp_int p, smat *P, smat *A, smat *G, qp_rea
 	k->D = alloc<qp_real>(N);
 	k->Lx = alloc<qp_real>(pl.Li.size() + 1);
 
-	{
-		std::lock_guard<std::mutex> guard(g_lock);
-		g_live[qp] = Registered{cached, dense};
-	}
 	qp->stats->ldl_numeric = 0.0;
 	qp->stats->tsetup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 	return qp;
@@ -210,10 +245,6 @@ void free_smat_owned(smat *M)
 void cleanup_common(QP *qp, bool dense)
 {
 	if (!qp) return;
-	{
-		std::lock_guard<std::mutex> guard(g_lock);
-		g_live.erase(qp);
-	}
 	free(qp->x); free(qp->y); free(qp->z); free(qp->s);
 	free(qp->rx); free(qp->ry); free(qp->rz);
 	free(qp->delta); free(qp->delta_x); free(qp->delta_y); free(qp->delta_z); free(qp->delta_s);
@@ -227,7 +258,8 @@ void cleanup_common(QP *qp, bool dense)
 	free(k->b); free(k->Parent); free(k->Flag); free(k->Lnz); free(k->Li); free(k->Lp); free(k->Lti); free(k->Ltp);
 	free(k->Pattern); free(k->UPattern); free(k->Y); free(k->Lx); free(k->D); free(k->Pinv);
 	if (qp->stats->AMD_RESULT != -3) free(k->P);
-	free(k);
+	if (KktBlock *blk = block_of(qp)) delete blk; // (drops the QP's reference to its plan)
+	else free(k);
 	free(qp->options);
 	free(qp->stats);
 	free(qp);
@@ -256,26 +288,24 @@ qp_int QP_SOLVE(QP *qp)
 		printf("****qpSWIFT : Sparse Quadratic Programming Solver****\n\n");
 		printf("================Data Statistics======================\n");
 	}
-	std::shared_ptr<CachedPlan> cached;
-	{
-		std::lock_guard<std::mutex> guard(g_lock);
-		auto it = g_live.find(qp);
-		if (it != g_live.end()) cached = it->second.plan;
-	}
+	KktBlock *blk = block_of(qp);
+	std::shared_ptr<CachedPlan> cached = blk ? blk->plan : nullptr;
 	qp->stats->Flag = QP_FATAL;
 	qp_int rc = QPB_E_ARG;
 	if (cached && cached->handle.plan.valid) {
-		{
-			std::lock_guard<std::mutex> guard(g_lock);
-			if (!cached->single && !cached->single_failed) {
-				cached->single = QPB_BATCH_CREATE(&cached->handle, qp->sigma_d, 1, -1);
-				if (!cached->single) cached->single_failed = true;
-			}
+		// One lock around sigma_d, the solve and its statistics: QPs of one pattern share the single-QP batch, and
+		// the reference allows independent QPs to be solved from different threads.
+		std::lock_guard<std::mutex> solving(cached->solve_lock);
+		if (!cached->single && !cached->single_failed) {
+			cached->single = QPB_BATCH_CREATE(&cached->handle, qp->sigma_d, 1, -1);
+			if (!cached->single) cached->single_failed = true;
 		}
 		if (cached->single) {
 			qp_int flag = QP_FATAL, iters = 0;
+			const bool verbose = qp->options->verbose > 0;
 			// sigma_d belongs to the QP, not to the cached plan
 			rc = QPB_BATCH_SET_SIGMA_D(cached->single, qp->sigma_d);
+			QPB_BATCH_ENABLE_TRACE(cached->single, 1); // per-iteration lines (verbose) and stats->ldl_numeric
 			rc = QP_SOLVE_BATCH(cached->single, 1, qp->options, qp->P->pr, qp->A ? qp->A->pr : nullptr, qp->G->pr, qp->c, qp->h, qp->b, qp->x, qp->y, qp->z, qp->s, &flag, &iters);
 			if (rc >= 0) {
 				qp_real fval = 0.0, st[8];
@@ -290,6 +320,19 @@ qp_int QP_SOLVE(QP *qp)
 				qp->stats->IterationCount = iters;
 				qp->stats->kkt_time = QPB_BATCH_LAST_KERNEL_MS(cached->single) * 1e-3;
 				qp->stats->resolve_kkt = 0;
+				std::vector<qp_real> trace((size_t)(qp->options->maxit + 2) * 8, 0.0);
+				if (QPB_BATCH_READ_TRACE(cached->single, 1, qp->options->maxit, trace.data()) == 0) {
+					qp->stats->ldl_numeric += trace[0]; // time inside LDL_numeric (Auxilary.c:476-484), device clock
+					if (verbose) {
+						// the reference's per-iteration lines (qpSWIFT.c:513-516, 598-601), printed after the fact
+						const qp_int shown = flag == QP_OPTIMAL ? iters + 1 : iters;
+						for (qp_int it = 0; it < shown; ++it) {
+							const qp_real *row = &trace[(size_t)(1 + it) * 8];
+							printf("It: %ld || pcost : %e || rx:%e   ||  ry:%e ||  rz:%e || mu:%e\n", it, row[0], row[1], row[2], row[3], row[4]);
+							if (it < iters) printf("      || Primal Step Size : %f || Dual Step Size   : %f\n", row[5], row[6]);
+						}
+					}
+				}
 			}
 		}
 	}
@@ -314,6 +357,14 @@ qp_int QP_SOLVE(QP *qp)
 		if (qp->stats->Flag == QP_KKTFAIL) printf("\nLDL Factorization fail\n\n");
 	}
 	return qp->stats->Flag;
+}
+
+// Introspection for the tests: 0 = plans in the (bounded) cache, 1 = its capacity.  There is nothing else to
+// count: the library keeps no table of QPs.
+qp_int QPB_PLAN_CACHE_INFO(int what)
+{
+	std::lock_guard<std::mutex> guard(g_lock);
+	return what == 0 ? (qp_int)g_plans.size() : (qp_int)PLAN_CACHE_SIZE;
 }
 
 void QP_CLEANUP(QP *qp) { cleanup_common(qp, false); }

@@ -59,6 +59,10 @@ struct BatchIO
 	const int *server_done;
 	// throughput kernel: where its last warp to leave announces that nothing more will be listed
 	int *done_ctas, *all_done; // (done_ctas counts warps)
+	// warp-per-QP kernel, verbose single solves: per QP (maxit + 2) rows of 8 doubles -- row 0: seconds spent in
+	// LDL_numeric (stats->ldl_numeric, Auxilary.c:476-484); row 1 + it: fval, n_rx, n_ry, n_rz, n_mu at the top of
+	// iteration it (qpSWIFT.c:513-516) and the step lengths it ends with (598-601).  Null: no trace.
+	double *trace;
 };
 
 #ifdef __CUDACC__
@@ -96,7 +100,8 @@ __device__ __forceinline__ PlanView view_of(const int *blob)
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
-// Coalesced copy of one QP's row, 128-bit when the row start is 16-byte aligned.
+// Coalesced copy of one QP's row, 128-bit when the row start is 16-byte aligned.  PLUS_ZERO: v + 0.0.
+template <bool PLUS_ZERO = false>
 __device__ __forceinline__ void warp_copy_in(double *dst, const double *__restrict__ src, int count)
 {
 	const int lane = lane_id();
@@ -104,10 +109,14 @@ __device__ __forceinline__ void warp_copy_in(double *dst, const double *__restri
 		const int pairs = count >> 1;
 		const double2 *s2 = reinterpret_cast<const double2 *>(src);
 		double2 *d2 = reinterpret_cast<double2 *>(dst);
-		for (int i = lane; i < pairs; i += 32) d2[i] = __ldg(s2 + i);
-		if ((count & 1) && lane == 0) dst[count - 1] = __ldg(src + count - 1);
+		for (int i = lane; i < pairs; i += 32) {
+			double2 v = __ldg(s2 + i);
+			if (PLUS_ZERO) { v.x += 0.0; v.y += 0.0; }
+			d2[i] = v;
+		}
+		if ((count & 1) && lane == 0) dst[count - 1] = PLUS_ZERO ? __ldg(src + count - 1) + 0.0 : __ldg(src + count - 1);
 	} else {
-		for (int i = lane; i < count; i += 32) dst[i] = __ldg(src + i);
+		for (int i = lane; i < count; i += 32) dst[i] = PLUS_ZERO ? __ldg(src + i) + 0.0 : __ldg(src + i);
 	}
 }
 

@@ -45,6 +45,13 @@ const GeneratedWarpKernel *find_generated_warp_kernel(unsigned long long key);
 
 #ifdef __CUDACC__
 
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
 // One table-driven chain per lane (generated programs): acc -= S[ta[64 t]] * S[tb[64 t]], t ascending; ta / tb
 // point at the lane's column of 16-bit byte offsets, a step's rows of 32 lie 64 entries apart.
 __device__ __forceinline__ double lane_chain(double acc, const unsigned sb, const unsigned short *__restrict__ ta, const unsigned short *__restrict__ tb, const int steps)
@@ -92,6 +99,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 	double sigma = 0.0, mu = 0.0, ap = 0.0, ad = 0.0;
 	Scalars sc;
 	sc.n_rx = sc.n_ry = sc.n_rz = sc.n_mu = sc.fval = 0.0;
+	const size_t trace_rows = (size_t)prm.maxit + 2;
+	long long ldl_ns = 0;
 
 	for (;;) {
 		int mode = MODE_IDLE;
@@ -105,9 +114,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 				const IterSums sums = ipm_sums(n, m, p, sb, lay, lay.T);
 				sc = sums.sc;
 				mu_next = sums.mu;
+				if (io.trace && lane == 0) {
+					double *row = io.trace + ((size_t)q * trace_rows + 1 + iters) * 8;
+					row[0] = sc.fval; row[1] = sc.n_rx; row[2] = sc.n_ry; row[3] = sc.n_rz; row[4] = sc.n_mu;
+				}
 				if (sc.n_rx < thr && sc.n_rz < thr && (p == 0 || sc.n_ry < thr) && sc.n_mu < prm.abstol) flag = 0;
 			}
 			if (flag >= 0) {
+				if (io.trace && lane == 0) io.trace[(size_t)q * trace_rows * 8] = (double)ldl_ns * 1e-9;
 				const size_t qi = (size_t)q;
 				warp_copy_out(io.x ? io.x + qi * n : nullptr, w.x, n);
 				if (p) warp_copy_out(io.y ? io.y + qi * p : nullptr, w.y, p);
@@ -162,9 +176,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 				const int resume_at = packed ? (q >> 24) : 0; // > 0: a straggler's iterate is waiting in the output arrays
 				if (packed) q &= (1 << 24) - 1;
 				const size_t qi = (size_t)q;
-				warp_copy_in(w.V, io.Ppr + qi * pv.offA, pv.offA);
-				if (p) warp_copy_in(w.V + pv.offA, io.Apr + qi * (pv.offG - pv.offA), pv.offG - pv.offA);
-				warp_copy_in(w.V + pv.offG, io.Gpr + qi * (pv.nV - pv.offG), pv.nV - pv.offG);
+				// matrix values as v + 0.0 (-0.0 becomes +0.0): what "Y[i] += value" from Y[i] == 0 makes of them (ldl.c:284)
+				warp_copy_in<true>(w.V, io.Ppr + qi * pv.offA, pv.offA);
+				if (p) warp_copy_in<true>(w.V + pv.offA, io.Apr + qi * (pv.offG - pv.offA), pv.offG - pv.offA);
+				warp_copy_in<true>(w.V + pv.offG, io.Gpr + qi * (pv.nV - pv.offG), pv.nV - pv.offG);
 				warp_copy_in(w.c, io.c + qi * n, n);
 				warp_copy_in(w.h, io.h + qi * m, m);
 				if (p) warp_copy_in(w.b, io.b + qi * p, p);
@@ -184,6 +199,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 					may_leave = false;
 				} else {
 					ipm_init_rhs(pv, w);
+					ldl_ns = 0;
 					iters = 0;
 					sigma = prm.sigma0;
 					mu = ap = ad = 0.0;
@@ -200,7 +216,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 		}
 
 		if (mode != MODE_IDLE) {
+			long long t0 = 0;
+			if (io.trace) t0 = (long long)globaltimer_ns();
 			PROG::factor(pg, sb, busy);
+			if (io.trace) ldl_ns += (long long)globaltimer_ns() - t0;
 			PROG::solve(pg, sb, busy);
 		}
 		if (mode == MODE_INIT) {
@@ -216,6 +235,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 		if (mode == MODE_PRED || mode == MODE_CENT) { // step, damping, update (qpSWIFT.c:584-596)
 			ipm_recover_and_steplength(n, m, p, w, ap, ad);
 			ipm_update(n, m, p, w, ap, ad);
+			if (io.trace && lane == 0) {
+				double *row = io.trace + ((size_t)q * trace_rows + 1 + iters) * 8;
+				row[5] = ap; row[6] = ad;
+			}
 			++iters;
 		}
 	}

@@ -62,8 +62,8 @@ EXPORTS = [
     "QPB_PLAN_LAYOUT", "QPB_PLAN_STREAM", "QPB_PLAN_STREAM_INFO", "QPB_PLAN_STREAM_KEY", "QPB_GENERATED_KERNELS",
     "QP_SETUP_BATCH", "QPB_BATCH_CREATE", "QP_SOLVE_BATCH", "QP_SOLVE_BATCH_DEVICE", "QP_CLEANUP_BATCH",
     "QP_SOLVE_BATCH_DENSE", "QPB_DENSE_TO_VALUES_DEVICE",
-    "QPB_BATCH_READ_STATS", "QPB_BATCH_SET_SIGMA_D", "QPB_BATCH_LAST_KERNEL_MS", "QPB_BATCH_LAST_LAUNCHES", "QPB_BATCH_LAST_KERNEL",
-    "QPB_LDL_NUMERIC_BATCH", "QPB_LDL_SOLVE_BATCH", "QPB_LAST_ERROR", "QPB_DEVICE_COUNT",
+    "QPB_BATCH_READ_STATS", "QPB_BATCH_SET_SIGMA_D", "QPB_BATCH_ENABLE_TRACE", "QPB_BATCH_READ_TRACE", "QPB_BATCH_LAST_KERNEL_MS", "QPB_BATCH_LAST_LAUNCHES", "QPB_BATCH_LAST_KERNEL",
+    "QPB_LDL_NUMERIC_BATCH", "QPB_LDL_SOLVE_BATCH", "QPB_LAST_ERROR", "QPB_DEVICE_COUNT", "QPB_PLAN_CACHE_INFO",
 ]
 
 _lib = None
@@ -121,6 +121,10 @@ def lib():
         lb.QP_CLEANUP_BATCH.argtypes = [V]
         lb.QPB_BATCH_READ_STATS.restype = L
         lb.QPB_BATCH_READ_STATS.argtypes = [V, L, V, V]
+        lb.QPB_BATCH_ENABLE_TRACE.restype = L
+        lb.QPB_BATCH_ENABLE_TRACE.argtypes = [V, C.c_int]
+        lb.QPB_BATCH_READ_TRACE.restype = L
+        lb.QPB_BATCH_READ_TRACE.argtypes = [V, L, L, V]
         lb.QPB_BATCH_SET_SIGMA_D.restype = L
         lb.QPB_BATCH_SET_SIGMA_D.argtypes = [V, D]
         lb.QPB_BATCH_LAST_KERNEL_MS.restype = D
@@ -133,6 +137,8 @@ def lib():
         lb.QPB_LDL_NUMERIC_BATCH.argtypes = [V, L, V, V, V, V, V]
         lb.QPB_LDL_SOLVE_BATCH.restype = L
         lb.QPB_LDL_SOLVE_BATCH.argtypes = [V, L, V, V, V, V, V]
+        lb.QPB_PLAN_CACHE_INFO.restype = L
+        lb.QPB_PLAN_CACHE_INFO.argtypes = [C.c_int]
         lb.QPB_LAST_ERROR.restype = C.c_char_p
         lb.QPB_DEVICE_COUNT.restype = C.c_int
         _lib = lb
@@ -382,7 +388,7 @@ class BatchSolver:
             pass
 
 
-def solve_single(pat, Ppr, Apr, Gpr, c, h, b, *, sigma_d=0.0, permut=None, maxit=None, reltol=None, abstol=None):
+def solve_single(pat, Ppr, Apr, Gpr, c, h, b, *, sigma_d=0.0, permut=None, maxit=None, reltol=None, abstol=None, verbose=None, cleanup=True):
     """``QP_SETUP`` + ``QP_SOLVE`` + ``QP_CLEANUP`` for one instance, exactly as a C caller would."""
     lb = lib()
     keep = [_i64(a) for a in (pat.Pjc, pat.Pir, pat.Ajc, pat.Air, pat.Gjc, pat.Gir)]
@@ -400,6 +406,8 @@ def solve_single(pat, Ppr, Apr, Gpr, c, h, b, *, sigma_d=0.0, permut=None, maxit
         o.reltol = float(reltol)
     if abstol is not None:
         o.abstol = float(abstol)
+    if verbose is not None:
+        o.verbose = int(verbose)
     flag = int(lb.QP_SOLVE(qp_p))
     grab = lambda ptr, k: np.ctypeslib.as_array(ptr, shape=(k,)).copy() if k else np.zeros(0)
     st = qp.stats.contents
@@ -407,5 +415,6 @@ def solve_single(pat, Ppr, Apr, Gpr, c, h, b, *, sigma_d=0.0, permut=None, maxit
            "s": grab(qp.s, qp.m), "flag": flag, "iters": int(st.IterationCount), "fval": float(st.fval),
            "stats": {f: getattr(st, f) for f, _ in stats._fields_}, "sigma": o.sigma,
            "P": np.ctypeslib.as_array(qp.kkt.contents.P, shape=(pat.N,)).copy()}
-    lb.QP_CLEANUP(qp_p)
+    if cleanup:
+        lb.QP_CLEANUP(qp_p)
     return out

@@ -152,13 +152,23 @@ qp_int QPB_BATCH_READ_STATS(QPBatch *batch, qp_int count, qp_real *fval, qp_real
 /* sigma_d belongs to a QP, not to its pattern: change it between solves. */
 qp_int QPB_BATCH_SET_SIGMA_D(QPBatch *batch, qp_real sigma_d);
 
+/* Per-iteration trace of the next host-pointer solves on this batch (small capacities only: the warp-per-QP
+ * kernel keeps it, the throughput kernel does not).  QPB_BATCH_READ_TRACE copies trace[count][maxit + 2][8]:
+ * row 0 = {seconds in LDL_numeric (stats->ldl_numeric, Auxilary.c:476-484), 0...}; row 1 + it =
+ * {fval, n_rx, n_ry, n_rz, n_mu at the top of iteration it (qpSWIFT.c:513-516), alpha_p, alpha_d of its step
+ * (qpSWIFT.c:598-601), 0}.  QP_SOLVE uses it for verbose > 0. */
+qp_int QPB_BATCH_ENABLE_TRACE(QPBatch *batch, int on);
+qp_int QPB_BATCH_READ_TRACE(QPBatch *batch, qp_int count, qp_int maxit, qp_real *trace);
+
 double QPB_BATCH_LAST_KERNEL_MS(const QPBatch *batch);
 qp_int QPB_BATCH_LAST_LAUNCHES(const QPBatch *batch);
-/* Which kernel the last solve used: 0 = latency kernel (one QP per warp, working set in shared
- * memory; small batches), 1 = throughput kernel (one QP per thread, working sets interleaved in HBM;
- * batches of at least QPB_STREAM_MIN [default 2048] QPs) interpreting the pattern's micro-programs,
- * 2 = the throughput kernel specialised for the pattern (micro-programs compiled into straight-line
- * code, see QPB_PLAN_STREAM_KEY). */
+/* Which kernel the last solve used: 0 = warp-per-QP kernel (one QP per warp, working set in shared memory)
+ * interpreting the pattern's wave schedules, 1 = throughput kernel (one QP per thread, working sets
+ * interleaved in HBM) interpreting the pattern's micro-programs, 2 = the throughput kernel specialised for the
+ * pattern (straight-line code, see QPB_PLAN_STREAM_KEY), 3 = the warp-per-QP kernel specialised for the pattern
+ * (lane = row of L, factor resident in shared memory).  Dispatch: the throughput kernel takes batches of at
+ * least QPB_STREAM_MIN QPs [default 2048; 113,664 = three waves of its lanes where the library carries a
+ * specialised warp-per-QP kernel for the pattern], the warp-per-QP kernel everything smaller. */
 int QPB_BATCH_LAST_KERNEL(const QPBatch *batch);
 
 /* ---------------------------------------------------------------------------------------------
@@ -173,6 +183,10 @@ qp_int QPB_LDL_NUMERIC_BATCH(QPBatch *batch, qp_int count, const qp_real *dvals,
 /* LDL_perm, lsolve, dsolve, ltsolve, permt (ldl.c:495-597) for `count` QPs:
  * rhs[count][N] -> sol[count][N] (may alias). */
 qp_int QPB_LDL_SOLVE_BATCH(QPBatch *batch, qp_int count, const qp_real *dLx, const qp_real *dD, const qp_real *drhs, qp_real *dsol, void *stream);
+
+/* QP_SETUP caches the symbolic plan (and the single-QP batch) per sparsity pattern; the cache is bounded and
+ * evicts the least recently used plan.  what = 0: plans cached now, 1: the cache's capacity. */
+qp_int QPB_PLAN_CACHE_INFO(int what);
 
 const char *QPB_LAST_ERROR(void);
 int QPB_DEVICE_COUNT(void);

@@ -129,7 +129,7 @@ def _plan_of(qp) -> dict:
 
 
 def solve_sparse(pat, Ppr, Apr, Gpr, c, h, b, *, kind=None, sigma_d=0.0, permut=None, maxit=None, reltol=None,
-                 abstol=None, want_factor=False) -> Solution:
+                 abstol=None, want_factor=False, verbose=None) -> Solution:
     """``QP_SETUP`` (CCS, shared pattern) + ``QP_SOLVE`` + ``QP_CLEANUP`` for ONE instance."""
     kind = kind or best_kind()
     lb = lib(kind)
@@ -158,6 +158,8 @@ def solve_sparse(pat, Ppr, Apr, Gpr, c, h, b, *, kind=None, sigma_d=0.0, permut=
         o.reltol = float(reltol)
     if abstol is not None:
         o.abstol = float(abstol)
+    if verbose is not None:
+        o.verbose = int(verbose)
     flag = int(lb.QP_SOLVE(qp_p))
     st = qp.stats.contents
     stats = {f: getattr(st, f) for f, _ in Stats._fields_}

@@ -17,7 +17,7 @@ def make_slice(lay, batch, i):
     S[lay["zero"]] = 0.0
     S[lay["zero"] + 1] = -0.0
     vals = np.concatenate([batch.Ppr[i], batch.Apr[i], batch.Gpr[i]])
-    S[lay["V"]:lay["V"] + vals.size] = vals
+    S[lay["V"]:lay["V"] + vals.size] = vals + 0.0  # (the kernel normalises -0.0 to +0.0 when it loads the values)
     S[lay["c"]:lay["c"] + pat.n] = batch.c[i]
     S[lay["h"]:lay["h"] + pat.m] = batch.h[i]
     S[lay["b"]:lay["b"] + pat.p] = batch.b[i]
