@@ -42,11 +42,16 @@ def _residual_norms(batch, out):
     return norm(rx), norm(ry), norm(rz), (s * z).sum(axis=1) / pat.m
 
 
-def test_full_size_batch_properties(qps, oracle):
+@pytest.mark.parametrize("kernel", ["warp", "stream"])
+def test_full_size_batch_properties(qps, oracle, monkeypatch, kernel):
+    """configs[1] at full size on the kernel the library picks for it (the specialised warp-per-QP kernel) and on the
+    throughput kernel (QPB_STREAM_MIN as for patterns without a specialised warp kernel)."""
+    if kernel == "stream":
+        monkeypatch.setenv("QPB_STREAM_MIN", "2048")
     batch = dogbot.generate("trot", COUNT)
     solver = qps.BatchSolver(batch.pattern, COUNT)
     out = solver.solve(batch)
-    assert solver.last_kernel == "stream" and solver.last_kernel_generated
+    assert solver.last_kernel == kernel and solver.last_kernel_generated
     ok = out["flag"] == qps.QP_OPTIMAL
     assert ok.mean() > 0.99 and set(np.unique(out["flag"])) <= {qps.QP_OPTIMAL, qps.QP_MAXIT}
     assert 8 <= out["iters"][ok].min() and out["iters"][ok].max() <= 40
