@@ -11,7 +11,7 @@ SRC      := apf_quadruped_b200/csrc
 OBJ      := build/obj
 LIB      := apf_quadruped_b200/lib/libqpswift_b200.so
 
-HOST_SRCS := $(SRC)/amd_order.cpp $(SRC)/symbolic.cpp $(SRC)/program.cpp $(SRC)/stream_program.cpp $(SRC)/capi_plan.cpp $(SRC)/capi_qp.cpp
+HOST_SRCS := $(SRC)/amd_order.cpp $(SRC)/symbolic.cpp $(SRC)/program.cpp $(SRC)/stream_program.cpp $(SRC)/capi_plan.cpp $(SRC)/capi_qp.cpp $(SRC)/multi.cpp
 HOST_OBJS := $(patsubst $(SRC)/%.cpp,$(OBJ)/%.o,$(HOST_SRCS))
 CU_SRCS   := $(SRC)/batch.cu
 CU_OBJS   := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(CU_SRCS))
@@ -29,6 +29,7 @@ all:
 	$(MAKE) gen
 	$(MAKE) $(LIB)
 	$(MAKE) oracle
+	$(MAKE) ctest
 
 $(OBJ)/%.o: $(SRC)/%.cpp $(wildcard $(SRC)/*.h) $(wildcard include/*.h include/qpSWIFT/*.h)
 	@mkdir -p $(OBJ)
@@ -48,13 +49,18 @@ gen:
 
 $(LIB): $(HOST_OBJS) $(CU_OBJS) $(GEN_OBJS)
 	@mkdir -p $(dir $(LIB))
-	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart shared
+	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart shared -ldl -lpthread
 
 oracle:
 	$(MAKE) -C oracle all
 
+# the C caller of the multi-GPU entry points (tests/test_multi_gpu.py runs it on the GPU box)
+ctest: tests/c/multi_gpu_test
+tests/c/multi_gpu_test: tests/c/multi_gpu_test.c $(LIB) include/qpswift_b200.h
+	gcc -O2 -std=gnu99 -Wall -Iinclude -o $@ $< -L$(dir $(LIB)) -lqpswift_b200 -Wl,-rpath,'$$ORIGIN/../../apf_quadruped_b200/lib'
+
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) tests/c/multi_gpu_test
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean gen
+.PHONY: all oracle clean gen ctest

@@ -413,7 +413,7 @@ static int launch_fused(QPBatch *B, BatchIO io, const settings *opts, cudaStream
 	io.spill_sigma = nullptr;
 	io.server_done = nullptr;
 	io.done_ctas = io.all_done = nullptr;
-	if (!(B->d_workspace && io.count >= B->stream_min)) io.ready = nullptr; // only the throughput kernel waits for rows
+	if (!(B->d_workspace && io.count >= B->stream_min) && !B->gen_warp) io.ready = nullptr; // (the interpreted warp-per-QP kernel takes whole batches only)
 	CUDA_TRY(cudaMemsetAsync(B->d_counter, 0, sizeof(int), st));
 	if (B->d_workspace && io.count >= B->stream_min) return launch_stream(B, io, prm, st);
 	B->last_kernel = B->gen_warp ? 3 : 0;
@@ -619,7 +619,9 @@ static qp_int qp_solve_batch_host(QPBatch *B, qp_int count, const settings *opts
 	// device's address space): the throughput kernel writes a finished QP's rows 256 bytes at a time over the
 	// bus while the others are still being solved, instead of one copy of everything after the kernel.
 	bool direct[4] = {false, false, false, false};
-	if (B->d_workspace && count >= B->stream_min && !getenv("QPB_NO_OVERLAP")) {
+	// (both the throughput kernel and the specialised warp-per-QP kernel take QPs in index order from a queue)
+	const bool overlap = ((B->d_workspace && count >= B->stream_min) || (B->gen_warp && count >= 4096)) && !getenv("QPB_NO_OVERLAP");
+	if (overlap) {
 		qp_real *host_out[4] = {x, y, z, s};
 		double **dev_out[4] = {&io.x, &io.y, &io.z, &io.s};
 		for (int k = 0; k < 4; ++k) {
@@ -631,7 +633,6 @@ static qp_int qp_solve_batch_host(QPBatch *B, qp_int count, const settings *opts
 			} else cudaGetLastError(); // (an unregistered pointer is not an error here)
 		}
 	}
-	const bool overlap = B->d_workspace && count >= B->stream_min && !getenv("QPB_NO_OVERLAP");
 	if (!overlap) {
 		for (int i = 0; i < 6; ++i)
 			if (widths[i]) CUDA_TRY(cudaMemcpyAsync(B->d_in[i], src[i], n * widths[i] * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -759,6 +760,12 @@ qp_int QPB_BATCH_READ_TRACE(QPBatch *B, qp_int count, qp_int maxit, qp_real *tra
 	CUDA_TRY(cudaSetDevice(B->device));
 	CUDA_TRY(cudaMemcpy(trace, B->d_trace, (size_t)count * B->trace_rows * 8 * sizeof(double), cudaMemcpyDeviceToHost));
 	return 0;
+}
+
+void QPB_BATCH_ROW_WIDTHS(const QPBatch *B, qp_int *nnz)
+{
+	if (!B || !nnz) return;
+	nnz[0] = B->plan.nnzP; nnz[1] = B->plan.nnzA; nnz[2] = B->plan.nnzG;
 }
 
 double QPB_BATCH_LAST_KERNEL_MS(const QPBatch *B) { return B ? B->last_kernel_ms : 0.0; }

@@ -101,7 +101,9 @@ __device__ __forceinline__ PlanView view_of(const int *blob)
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 // Coalesced copy of one QP's row, 128-bit when the row start is 16-byte aligned.  PLUS_ZERO: v + 0.0.
-template <bool PLUS_ZERO = false>
+// L2_ONLY: ld.global.cg -- rows that a copy engine writes WHILE the kernel runs (host-pointer entry, batch.cu) must
+// not be served from an L1 sector that an earlier read of the neighbouring row brought in before they arrived.
+template <bool PLUS_ZERO = false, bool L2_ONLY = false>
 __device__ __forceinline__ void warp_copy_in(double *dst, const double *__restrict__ src, int count)
 {
 	const int lane = lane_id();
@@ -110,13 +112,19 @@ __device__ __forceinline__ void warp_copy_in(double *dst, const double *__restri
 		const double2 *s2 = reinterpret_cast<const double2 *>(src);
 		double2 *d2 = reinterpret_cast<double2 *>(dst);
 		for (int i = lane; i < pairs; i += 32) {
-			double2 v = __ldg(s2 + i);
+			double2 v = L2_ONLY ? __ldcg(s2 + i) : __ldg(s2 + i);
 			if (PLUS_ZERO) { v.x += 0.0; v.y += 0.0; }
 			d2[i] = v;
 		}
-		if ((count & 1) && lane == 0) dst[count - 1] = PLUS_ZERO ? __ldg(src + count - 1) + 0.0 : __ldg(src + count - 1);
+		if ((count & 1) && lane == 0) {
+			const double t = L2_ONLY ? __ldcg(src + count - 1) : __ldg(src + count - 1);
+			dst[count - 1] = PLUS_ZERO ? t + 0.0 : t;
+		}
 	} else {
-		for (int i = lane; i < count; i += 32) dst[i] = PLUS_ZERO ? __ldg(src + i) + 0.0 : __ldg(src + i);
+		for (int i = lane; i < count; i += 32) {
+			const double t = L2_ONLY ? __ldcg(src + i) : __ldg(src + i);
+			dst[i] = PLUS_ZERO ? t + 0.0 : t;
+		}
 	}
 }
 

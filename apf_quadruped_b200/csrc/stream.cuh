@@ -216,7 +216,7 @@ __device__ __forceinline__ void stream_take_row(double *to, const double *row, c
 	for (int e0 = lane; e0 < count; e0 += 8 * 32) {
 		double v[8];
 #pragma unroll
-		for (int j = 0; j < 8; ++j) v[j] = row[min(e0 + 32 * j, count - 1)];
+		for (int j = 0; j < 8; ++j) v[j] = __ldcg(row + min(e0 + 32 * j, count - 1)); // (L2 only: rows may arrive while the kernel runs)
 #pragma unroll
 		for (int j = 0; j < 8; ++j)
 			if (e0 + 32 * j < count) to[(size_t)(e0 + 32 * j) << 5] = PLUS_ZERO ? v[j] + 0.0 : v[j];
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(STREAM_MAX_WARPS * 32, 1) qp_solve_stream_kern
 				stream_take_row<false>(to + ((size_t)L.c << 5), io.c + qi * n, n, lane);
 				stream_take_row<false>(to + ((size_t)L.h << 5), io.h + qi * m, m, lane);
 				for (int e = lane; e < p; e += 32) {
-					const double be = io.b[qi * p + e];
+					const double be = __ldcg(io.b + qi * p + e);
 					to[(L.b + e) << 5] = be;
 					to[(L.nb + e) << 5] = -be;
 				}

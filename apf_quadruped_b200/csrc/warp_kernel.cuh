@@ -176,13 +176,28 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 				const int resume_at = packed ? (q >> 24) : 0; // > 0: a straggler's iterate is waiting in the output arrays
 				if (packed) q &= (1 << 24) - 1;
 				const size_t qi = (size_t)q;
+				// host-pointer entry: the value rows come up in chunks while the kernel runs (batch.cu); QPs [0, *ready) are there
+				if (io.ready && !io.index) {
+					if (lane == 0)
+						while (*reinterpret_cast<const volatile int *>(io.ready) <= q) __nanosleep(500);
+					__syncwarp();
+				}
 				// matrix values as v + 0.0 (-0.0 becomes +0.0): what "Y[i] += value" from Y[i] == 0 makes of them (ldl.c:284)
-				warp_copy_in<true>(w.V, io.Ppr + qi * pv.offA, pv.offA);
-				if (p) warp_copy_in<true>(w.V + pv.offA, io.Apr + qi * (pv.offG - pv.offA), pv.offG - pv.offA);
-				warp_copy_in<true>(w.V + pv.offG, io.Gpr + qi * (pv.nV - pv.offG), pv.nV - pv.offG);
-				warp_copy_in(w.c, io.c + qi * n, n);
-				warp_copy_in(w.h, io.h + qi * m, m);
-				if (p) warp_copy_in(w.b, io.b + qi * p, p);
+				if (io.ready) { // (rows that arrive while the kernel runs: L2 only)
+					warp_copy_in<true, true>(w.V, io.Ppr + qi * pv.offA, pv.offA);
+					if (p) warp_copy_in<true, true>(w.V + pv.offA, io.Apr + qi * (pv.offG - pv.offA), pv.offG - pv.offA);
+					warp_copy_in<true, true>(w.V + pv.offG, io.Gpr + qi * (pv.nV - pv.offG), pv.nV - pv.offG);
+					warp_copy_in<false, true>(w.c, io.c + qi * n, n);
+					warp_copy_in<false, true>(w.h, io.h + qi * m, m);
+					if (p) warp_copy_in<false, true>(w.b, io.b + qi * p, p);
+				} else {
+					warp_copy_in<true>(w.V, io.Ppr + qi * pv.offA, pv.offA);
+					if (p) warp_copy_in<true>(w.V + pv.offA, io.Apr + qi * (pv.offG - pv.offA), pv.offG - pv.offA);
+					warp_copy_in<true>(w.V + pv.offG, io.Gpr + qi * (pv.nV - pv.offG), pv.nV - pv.offG);
+					warp_copy_in(w.c, io.c + qi * n, n);
+					warp_copy_in(w.h, io.h + qi * m, m);
+					if (p) warp_copy_in(w.b, io.b + qi * p, p);
+				}
 				__syncwarp();
 				if (resume_at > 0 && io.spill_sigma) {
 					// the state of QP_SOLVE's loop between two iterations is (x, y, z, s, sigma, IterationCount);

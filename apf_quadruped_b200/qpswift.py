@@ -64,6 +64,8 @@ EXPORTS = [
     "QP_SOLVE_BATCH_DENSE", "QPB_DENSE_TO_VALUES_DEVICE",
     "QPB_BATCH_READ_STATS", "QPB_BATCH_SET_SIGMA_D", "QPB_BATCH_ENABLE_TRACE", "QPB_BATCH_READ_TRACE", "QPB_BATCH_LAST_KERNEL_MS", "QPB_BATCH_LAST_LAUNCHES", "QPB_BATCH_LAST_KERNEL",
     "QPB_LDL_NUMERIC_BATCH", "QPB_LDL_SOLVE_BATCH", "QPB_LAST_ERROR", "QPB_DEVICE_COUNT", "QPB_PLAN_CACHE_INFO",
+    "QPB_BATCH_ROW_WIDTHS", "QP_SETUP_BATCH_MULTI", "QPB_BATCH_CREATE_MULTI", "QPB_MULTI_DEVICES", "QPB_MULTI_SHARD",
+    "QP_SOLVE_BATCH_MULTI", "QP_SOLVE_BATCH_MULTI_DEVICE", "QP_CLEANUP_BATCH_MULTI", "QPB_MULTI_LAST_ERROR",
 ]
 
 _lib = None
@@ -139,6 +141,20 @@ def lib():
         lb.QPB_LDL_SOLVE_BATCH.argtypes = [V, L, V, V, V, V, V]
         lb.QPB_PLAN_CACHE_INFO.restype = L
         lb.QPB_PLAN_CACHE_INFO.argtypes = [C.c_int]
+        lb.QPB_BATCH_CREATE_MULTI.restype = V
+        lb.QPB_BATCH_CREATE_MULTI.argtypes = [V, L, L, L, D, L, C.POINTER(C.c_int), C.c_int]
+        lb.QP_SETUP_BATCH_MULTI.restype = V
+        lb.QP_SETUP_BATCH_MULTI.argtypes = [C.POINTER(QP), L, C.POINTER(C.c_int), C.c_int]
+        lb.QPB_MULTI_DEVICES.restype = C.c_int
+        lb.QPB_MULTI_DEVICES.argtypes = [V]
+        lb.QPB_MULTI_SHARD.restype = None
+        lb.QPB_MULTI_SHARD.argtypes = [V, L, C.c_int, PL, PL]
+        lb.QP_SOLVE_BATCH_MULTI.restype = L
+        lb.QP_SOLVE_BATCH_MULTI.argtypes = [V, L, C.POINTER(settings)] + [V] * 6 + [V] * 4 + [V, V]
+        lb.QP_SOLVE_BATCH_MULTI_DEVICE.restype = L
+        lb.QP_SOLVE_BATCH_MULTI_DEVICE.argtypes = [V, L, C.POINTER(settings)] + [V] * 15
+        lb.QP_CLEANUP_BATCH_MULTI.argtypes = [V]
+        lb.QPB_MULTI_LAST_ERROR.restype = C.c_char_p
         lb.QPB_LAST_ERROR.restype = C.c_char_p
         lb.QPB_DEVICE_COUNT.restype = C.c_int
         _lib = lb
@@ -378,6 +394,55 @@ class BatchSolver:
     def close(self):
         if getattr(self, "handle", None):
             lib().QP_CLEANUP_BATCH(self.handle)
+            self.handle = None
+        self.plan.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiSolver:
+    """``QP_SETUP_BATCH_MULTI`` / ``QP_SOLVE_BATCH_MULTI``: one batch cut into contiguous shards over several
+    devices inside the library (one host thread and one copy of the plan per device, no collective on the
+    host-pointer path)."""
+
+    def __init__(self, pattern, capacity: int, devices, sigma_d: float = 0.0, permut=None):
+        self.pattern = pattern
+        self.plan = Plan(pattern, permut)
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        self.handle = lib().QPB_BATCH_CREATE_MULTI(self.plan.handle, pattern.n, pattern.m, pattern.p, float(sigma_d), int(capacity), arr, len(self.devices))
+        if not self.handle:
+            raise RuntimeError(f"QPB_BATCH_CREATE_MULTI failed: {lib().QPB_MULTI_LAST_ERROR().decode()}")
+
+    def shard(self, count: int, d: int):
+        lo, hi = C.c_long(), C.c_long()
+        lib().QPB_MULTI_SHARD(self.handle, int(count), int(d), C.byref(lo), C.byref(hi))
+        return lo.value, hi.value
+
+    def solve(self, batch, opts: settings | None = None, out=None):
+        pat = self.pattern
+        cnt = batch.count
+        opts = opts or default_settings()
+        if out is None:
+            out = {"x": np.empty((cnt, pat.n)), "y": np.empty((cnt, pat.p)), "z": np.empty((cnt, pat.m)),
+                   "s": np.empty((cnt, pat.m)), "flag": np.empty(cnt, dtype=np.int64),
+                   "iters": np.empty(cnt, dtype=np.int64)}
+        arrs = [_f64(a) for a in (batch.Ppr, batch.Apr, batch.Gpr, batch.c, batch.h, batch.b)]
+        ptr = lambda a: a.ctypes.data if a.size else None
+        rc = lib().QP_SOLVE_BATCH_MULTI(self.handle, cnt, C.byref(opts), *[ptr(a) for a in arrs], ptr(out["x"]), ptr(out["y"]),
+                                        ptr(out["z"]), ptr(out["s"]), ptr(out["flag"]), ptr(out["iters"]))
+        if rc < 0:
+            raise RuntimeError(f"QP_SOLVE_BATCH_MULTI failed ({rc}): {lib().QPB_MULTI_LAST_ERROR().decode()}")
+        out["not_optimal"] = int(rc)
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().QP_CLEANUP_BATCH_MULTI(self.handle)
             self.handle = None
         self.plan.close()
 

@@ -143,6 +143,36 @@ qp_int QP_SOLVE_BATCH_DENSE(QPBatch *batch, qp_int count, const settings *opts, 
 
 void QP_CLEANUP_BATCH(QPBatch *batch);
 
+/* nnz[3] = entries of P, A, G per QP (the widths of the value rows Ppr / Apr / Gpr). */
+void QPB_BATCH_ROW_WIDTHS(const QPBatch *batch, qp_int *nnz);
+
+/* ---------------------------------------------------------------------------------------------
+ * The same batch split across several GPUs of one box, behind the C ABI (SURVEY.md 8b proposed
+ * QP_SETUP_BATCH(proto, batch, devices, ndev); the reference's caller is a C++ node, main.cpp:1649).
+ * QPs are independent, so the batch is cut into contiguous shards, one per entry of `devices` (the first
+ * count % ndev shards hold one QP more: QPB_MULTI_SHARD), every device solves its shard with its own copy
+ * of the plan, and nothing crosses devices during the solve.  Results are bit-identical for any ndev.
+ *   QP_SOLVE_BATCH_MULTI         host pointers (as QP_SOLVE_BATCH): every device reads its shard of the caller's
+ *                                arrays and writes its shard of the results -- no collective.  Returns the
+ *                                number of QPs whose flag is not QP_OPTIMAL, or a negative QPB_E_* code.
+ *   QP_SOLVE_BATCH_MULTI_DEVICE  arrays of ndev device pointers, entry d = shard d's rows in device d's memory
+ *                                (flags / iterations int32).  gx / gflag / giters (each may be NULL) receive, on
+ *                                EVERY device, the ncclAllGather of x [ndev][most][n], flags and iteration counts
+ *                                [ndev][most] (most = the largest shard; dx / dflag / diters must hold `most`
+ *                                rows; rows beyond a shard's count are padding) -- the only collective on the
+ *                                path, over one communicator per device (ncclCommInitAll).  Synchronous.
+ * A device may appear more than once in `devices` (shards then share it; no NCCL gather between them).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct QPBatchMulti QPBatchMulti;
+QPBatchMulti *QP_SETUP_BATCH_MULTI(const QP *proto, qp_int capacity, const int *devices, int ndev);
+QPBatchMulti *QPB_BATCH_CREATE_MULTI(const QPBPlan *plan, qp_int n, qp_int m, qp_int p, qp_real sigma_d, qp_int capacity, const int *devices, int ndev);
+int QPB_MULTI_DEVICES(const QPBatchMulti *multi);
+void QPB_MULTI_SHARD(const QPBatchMulti *multi, qp_int count, int shard, qp_int *lo, qp_int *hi);
+qp_int QP_SOLVE_BATCH_MULTI(QPBatchMulti *multi, qp_int count, const settings *opts, const qp_real *Ppr, const qp_real *Apr, const qp_real *Gpr, const qp_real *c, const qp_real *h, const qp_real *b, qp_real *x, qp_real *y, qp_real *z, qp_real *s, qp_int *flag, qp_int *iters);
+qp_int QP_SOLVE_BATCH_MULTI_DEVICE(QPBatchMulti *multi, qp_int count, const settings *opts, const qp_real *const *dPpr, const qp_real *const *dApr, const qp_real *const *dGpr, const qp_real *const *dc, const qp_real *const *dh, const qp_real *const *db, qp_real *const *dx, qp_real *const *dy, qp_real *const *dz, qp_real *const *ds, int *const *dflag, int *const *diters, qp_real *const *gx, int *const *gflag, int *const *giters);
+void QP_CLEANUP_BATCH_MULTI(QPBatchMulti *multi);
+const char *QPB_MULTI_LAST_ERROR(void);
+
 /* Device time (ms, CUDA events) of the kernels of the last QP_SOLVE_BATCH call and the number
  * of kernel launches it made. */
 /* fval[count] and stat[count][8] = {n_rx, n_ry, n_rz, n_mu, alpha_p, alpha_d, sigma, mu} of the last
