@@ -16,6 +16,7 @@
 #include "stream.cuh"
 #include "stream_gen.cuh"
 #include "warp_kernel.cuh"
+#include "wbc.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -192,6 +193,10 @@ struct QPBatch
 	double last_kernel_ms = 0.0;
 	long last_launches = 0;
 	int last_kernel = 0; // 0 warp-per-QP kernel (interpreted schedules), 1 throughput kernel (one QP per thread), 2 the same, pattern-specialised, 3 warp-per-QP kernel, pattern-specialised
+	// WBC formulation on the device (wbc.cuh): descriptor tables per contact pattern kind, built on first use
+	WbcDesc *d_wbc_desc = nullptr;
+	double *d_wbc_consts = nullptr;
+	WbcTables wbc;
 	std::mutex lock;
 };
 
@@ -467,6 +472,22 @@ __global__ void __launch_bounds__(256) dense_gather_kernel(const double *__restr
 	if (p) dense_gather_all(dA, mapA, (unsigned)(p * n), (unsigned)nnzA, oA, violation, (unsigned)first_qp, (unsigned)count * (unsigned)(p * n));
 }
 
+template <bool FUSED>
+__global__ void __launch_bounds__(1024) fp64_peak_kernel(double *sink, const int steps, const double b, const double c)
+{
+	double a[8];
+#pragma unroll
+	for (int k = 0; k < 8; ++k) a[k] = 1.0 + 1e-3 * (double)(threadIdx.x + k);
+	for (int i = 0; i < steps; ++i) {
+#pragma unroll
+		for (int k = 0; k < 8; ++k) a[k] = FUSED ? __fma_rn(a[k], b, c) : __dadd_rn(__dmul_rn(a[k], b), c);
+	}
+	double t = 0.0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) t += a[k];
+	sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+
 static int ensure_dense_maps(QPBatch *B, int ordering)
 {
 	if (B->d_dense_map[0] && B->dense_map_ordering == ordering) return 0;
@@ -539,6 +560,8 @@ void QP_CLEANUP_BATCH(QPBatch *B)
 	cudaFree(B->d_spill_sigma);
 	for (int k = 0; k < 3; ++k) { cudaFree(B->d_dense_map[k]); cudaFree(B->d_dense[k]); }
 	cudaFree(B->d_violation);
+	cudaFree(B->d_wbc_desc);
+	cudaFree(B->d_wbc_consts);
 	cudaFree(B->d_workspace);
 	cudaFree(B->d_trace);
 	cudaFree(B->d_spill);
@@ -574,6 +597,28 @@ qp_int QP_SOLVE_BATCH_DEVICE(QPBatch *B, qp_int count, const settings *opts, con
 	io.ready = nullptr;
 	io.trace = nullptr;
 	return launch_fused(B, io, opts, (cudaStream_t)stream);
+}
+
+// The QPs whose rows are listed in dindex[0 .. *dcount_ptr) (device memory; the count is read by the kernel, so a
+// list compacted on the device needs no host round trip and the launch can sit in a CUDA graph); rows = the
+// largest index + 1 the arrays hold.  Always the warp-per-QP kernel.
+qp_int QP_SOLVE_BATCH_DEVICE_INDEXED(QPBatch *B, qp_int rows, const settings *opts, const int *dindex, const int *dcount_ptr, const qp_real *dPpr, const qp_real *dApr, const qp_real *dGpr, const qp_real *dc, const qp_real *dh, const qp_real *db, qp_real *dx, qp_real *dy, qp_real *dz, qp_real *ds, int *dflag, int *diters, void *stream)
+{
+	if (!B || !opts || rows < 1 || rows > B->capacity || rows >= (1 << 24) || !dindex || !dcount_ptr || !dPpr || !dGpr || !dc || !dh || (B->plan.p && (!dApr || !db))) return fail(QPB_E_ARG, "QP_SOLVE_BATCH_DEVICE_INDEXED: bad argument (null pointer, rows > capacity)", cudaSuccess);
+	CUDA_TRY(cudaSetDevice(B->device));
+	BatchIO io;
+	io.Ppr = dPpr; io.Apr = dApr; io.Gpr = dGpr; io.c = dc; io.h = dh; io.b = db;
+	io.x = dx; io.y = dy; io.z = dz; io.s = ds; io.flag = dflag; io.iters = diters; io.fval = nullptr; io.stat = nullptr;
+	io.count = (int)rows;
+	io.index = dindex; io.count_ptr = dcount_ptr;
+	io.spill = nullptr; io.spill_count = nullptr; io.spill_sigma = nullptr; io.ready = nullptr; io.server_done = nullptr; io.done_ctas = io.all_done = nullptr; io.trace = nullptr;
+	SolveParams prm;
+	prm.maxit = (int)opts->maxit; prm.reltol = opts->reltol; prm.abstol = opts->abstol; prm.sigma0 = opts->sigma; prm.sigma_d = B->sigma_d; prm.spill_after = 0;
+	cudaStream_t st = (cudaStream_t)stream;
+	CUDA_TRY(cudaMemsetAsync(B->d_counter, 0, sizeof(int), st));
+	B->last_kernel = B->gen_warp ? 3 : 0;
+	B->last_launches = 1;
+	return launch_latency(B, io, prm, rows, B->d_counter, st);
 }
 
 qp_int QP_SOLVE_BATCH(QPBatch *B, qp_int count, const settings *opts, const qp_real *Ppr, const qp_real *Apr, const qp_real *Gpr, const qp_real *c, const qp_real *h, const qp_real *b, qp_real *x, qp_real *y, qp_real *z, qp_real *s, qp_int *flag, qp_int *iters)
@@ -760,6 +805,100 @@ qp_int QPB_BATCH_READ_TRACE(QPBatch *B, qp_int count, qp_int maxit, qp_real *tra
 	CUDA_TRY(cudaSetDevice(B->device));
 	CUDA_TRY(cudaMemcpy(trace, B->d_trace, (size_t)count * B->trace_rows * 8 * sizeof(double), cudaMemcpyDeviceToHost));
 	return 0;
+}
+
+// The descriptor table of `kind` for a plan's pattern (host only): desc[i] = op_a | b << 32 for every entry of the value
+// rows Ppr | Apr | Gpr | c | h | b, and the 32 constants behind the state row.  Returns the number of descriptors, or
+// QPB_E_PATTERN when the pattern is not that kind's.  Lets the tables be checked on the host (tests/test_wbc.py).
+qp_int QPB_WBC_DESCRIPTORS(const QPBPlan *plan, int kind, unsigned long long *desc, qp_int capacity, qp_real *consts)
+{
+	WbcTables T;
+	if (!plan || kind < 0 || kind > 2 || !wbc_build_tables(T, kind, plan->plan)) return fail(QPB_E_PATTERN, "QPB_WBC_DESCRIPTORS: not the DogBot pattern of that kind", cudaSuccess);
+	for (size_t i = 0; i < T.desc.size() && (qp_int)i < capacity; ++i) desc[i] = (unsigned long long)T.desc[i].op_a | ((unsigned long long)T.desc[i].b << 32);
+	if (consts)
+		for (int i = 0; i < WBC_SMEM - WBC_STATE; ++i) consts[i] = T.consts[i];
+	return (qp_int)T.desc.size();
+}
+
+static int ensure_wbc(QPBatch *B, int kind)
+{
+	if (B->d_wbc_desc && B->wbc.kind == kind) return 0;
+	if (B->d_wbc_desc) return fail(QPB_E_ARG, "WBC: this batch's pattern was bound to another contact pattern kind", cudaSuccess);
+	if (kind < 0 || kind > 2 || !wbc_build_tables(B->wbc, kind, B->plan)) { B->wbc.kind = -1; return fail(QPB_E_PATTERN, "WBC: the batch's sparsity pattern is not the DogBot pattern of that kind (0 stance, 1 trot, 2 crawl)", cudaSuccess); }
+	CUDA_TRY(cudaMalloc(&B->d_wbc_desc, B->wbc.desc.size() * sizeof(WbcDesc)));
+	CUDA_TRY(cudaMemcpy(B->d_wbc_desc, B->wbc.desc.data(), B->wbc.desc.size() * sizeof(WbcDesc), cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMalloc(&B->d_wbc_consts, sizeof(B->wbc.consts)));
+	CUDA_TRY(cudaMemcpy(B->d_wbc_consts, B->wbc.consts, sizeof(B->wbc.consts), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+qp_int QPB_WBC_FORMULATE_DEVICE(QPBatch *B, int kind, qp_int count, const qp_real *dstate, const int *dindex, const int *dcount_ptr, qp_real *dPpr, qp_real *dApr, qp_real *dGpr, qp_real *dc, qp_real *dh, qp_real *db, void *stream)
+{
+	if (!B || count < 0 || !dstate || !dPpr || !dApr || !dGpr || !dc || !dh || !db) return fail(QPB_E_ARG, "QPB_WBC_FORMULATE_DEVICE: bad argument", cudaSuccess);
+	if (count == 0) return 0;
+	CUDA_TRY(cudaSetDevice(B->device));
+	const int rc = ensure_wbc(B, kind);
+	if (rc) return rc;
+	const Plan &pl = B->plan;
+	WbcOut out;
+	out.Ppr = dPpr; out.Apr = dApr; out.Gpr = dGpr; out.c = dc; out.h = dh; out.b = db;
+	out.nnzP = (int)pl.nnzP; out.nnzA = (int)pl.nnzA; out.nnzG = (int)pl.nnzG; out.n = (int)pl.n; out.m = (int)pl.m; out.p = (int)pl.p;
+	const int warps = 8;
+	const long grid = std::min<long>((count + warps - 1) / warps, (long)B->sm_count * 6);
+	wbc_formulate_kernel<<<(unsigned)grid, warps * 32, warps * WBC_SMEM * sizeof(double), (cudaStream_t)stream>>>(dstate, B->d_wbc_desc, B->d_wbc_consts, out, dindex, dcount_ptr, (int)count);
+	CUDA_TRY(cudaGetLastError());
+	return 0;
+}
+
+qp_int QPB_WBC_TORQUES_DEVICE(QPBatch *B, int kind, qp_int count, const qp_real *dstate, const qp_real *dx, qp_real *dtau, const int *dindex, const int *dcount_ptr, void *stream)
+{
+	if (!B || count < 0 || !dstate || !dx || !dtau) return fail(QPB_E_ARG, "QPB_WBC_TORQUES_DEVICE: bad argument", cudaSuccess);
+	if (count == 0) return 0;
+	CUDA_TRY(cudaSetDevice(B->device));
+	const int rc = ensure_wbc(B, kind);
+	if (rc) return rc;
+	const int *st = B->wbc.stance_rows;
+	const long grid = std::min<long>((count * 12 + 255) / 256, (long)B->sm_count * 8);
+	wbc_torque_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(dstate, dx, dtau, B->wbc.nf, make_int4(st[0], st[1], st[2], st[3]), make_int4(st[4], st[5], st[6], st[7]), make_int4(st[8], st[9], st[10], st[11]), dindex, dcount_ptr, (int)count);
+	CUDA_TRY(cudaGetLastError());
+	return 0;
+}
+
+// FP64 peak of the device, measured: every thread runs 8 independent chains of a <- a * b + c, either as one
+// DFMA (fused != 0) or as DMUL + DADD, which is what this library's kernels execute (-fmad=false is part of the
+// arithmetic contract).  2 flops per step either way.  One CTA of 1024 threads per SM x 2, long enough to dwarf
+// the launch.  Returns TFLOP/s, or a negative QPB_E_* code.
+double QPB_FP64_PEAK(int device, int fused)
+{
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return (double)fail(QPB_E_NODEVICE, "no CUDA device", cudaSuccess);
+	if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return (double)fail(QPB_E_CUDA, "cudaSetDevice", cudaGetLastError());
+	cudaDeviceProp prop;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return (double)fail(QPB_E_CUDA, "cudaGetDeviceProperties", cudaGetLastError());
+	const int grid = prop.multiProcessorCount * 2, block = 1024, steps = 1 << 15;
+	double *sink = nullptr;
+	if (cudaMalloc(&sink, sizeof(double) * (size_t)grid * block) != cudaSuccess) return (double)fail(QPB_E_CUDA, "cudaMalloc", cudaGetLastError());
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	float best = 1e30f;
+	for (int rep = 0; rep < 4; ++rep) {
+		cudaEventRecord(e0, 0);
+		if (fused) fp64_peak_kernel<true><<<grid, block>>>(sink, steps, 1.0000001, 1e-9);
+		else fp64_peak_kernel<false><<<grid, block>>>(sink, steps, 1.0000001, 1e-9);
+		cudaEventRecord(e1, 0);
+		cudaEventSynchronize(e1);
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		if (rep > 0 && ms < best) best = ms;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(sink);
+	if (cudaGetLastError() != cudaSuccess) return (double)fail(QPB_E_CUDA, "fp64_peak_kernel", cudaGetLastError());
+	return 2.0 * 8.0 * (double)steps * (double)grid * block / (best * 1e-3) / 1e12;
 }
 
 void QPB_BATCH_ROW_WIDTHS(const QPBatch *B, qp_int *nnz)

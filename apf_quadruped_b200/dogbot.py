@@ -389,8 +389,75 @@ def generate(kind: str, count: int, start: int = 0, seed: int = DEFAULT_SEED) ->
     return Batch(pat, *out)
 
 
+def _fill_shared(kind, start, lo, hi, seed, names, count):
+    """Worker of generate_parallel: instances [lo, hi) of the range into the parent's shared buffers."""
+    from multiprocessing import resource_tracker, shared_memory
+    pat = pattern(kind)
+    widths = (pat.nnzP, pat.nnzA, pat.nnzG, pat.n, pat.m, pat.p)
+    step = 8 * CHUNK
+    views, keep = [], []
+    for name, w in zip(names, widths):
+        shm = shared_memory.SharedMemory(name=name)
+        resource_tracker.unregister(shm._name, "shared_memory")  # the parent owns the block
+        keep.append(shm)
+        views.append(np.ndarray((count, max(w, 1)), dtype=np.float64, buffer=shm.buf) if w else None)
+    at = lo
+    while at < hi:  # (piece by piece: bounded memory; cuts on the generator's chunk boundaries)
+        nxt = min(hi, ((start + at) // CHUNK + step // CHUNK) * CHUNK - start)
+        part = generate(kind, nxt - at, start + at, seed)
+        for v, a in zip(views, (part.Ppr, part.Apr, part.Gpr, part.c, part.h, part.b)):
+            if v is not None:
+                v[at:nxt] = a
+        at = nxt
+    del views
+    for shm in keep:
+        shm.close()
+
+
+def generate_parallel(kind: str, count: int, start: int = 0, seed: int = DEFAULT_SEED, procs: int | None = None) -> Batch:
+    """generate() on several host cores (large benchmark batches): the same instances, bit for bit -- instance i
+    depends on (seed, i) only -- written by worker processes (``python -m apf_quadruped_b200.dogbot fill ...``)
+    straight into shared buffers."""
+    import os
+    import subprocess
+    import sys
+    procs = procs or min(os.cpu_count() or 1, 32)
+    if count < 4 * CHUNK or procs <= 1:
+        return generate(kind, count, start, seed)
+    from multiprocessing import shared_memory
+    pat = pattern(kind)
+    widths = (pat.nnzP, pat.nnzA, pat.nnzG, pat.n, pat.m, pat.p)
+    blocks = [shared_memory.SharedMemory(create=True, size=max(8, 8 * count * max(w, 1))) for w in widths]
+    try:
+        names = [b.name for b in blocks]
+        # one contiguous range per worker, cut on the generator's chunk boundaries so that no chunk is drawn twice
+        first = start // CHUNK
+        chunks = (start + count + CHUNK - 1) // CHUNK - first
+        procs = max(1, min(procs, chunks))
+        cuts = [0] + [min(count, max(0, (first + (chunks * (w + 1)) // procs) * CHUNK - start)) for w in range(procs)]
+        cuts[-1] = count
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        workers = [subprocess.Popen([sys.executable, "-m", "apf_quadruped_b200.dogbot", "fill", kind, str(start), str(lo), str(hi), str(seed), str(count)] + names, cwd=root)
+                   for lo, hi in zip(cuts, cuts[1:]) if hi > lo]
+        for w in workers:
+            if w.wait() != 0:
+                raise RuntimeError("dogbot.generate_parallel: a worker failed")
+        out = [np.ndarray((count, w), dtype=np.float64, buffer=b.buf).copy() if w else np.empty((count, 0)) for b, w in zip(blocks, widths)]
+    finally:
+        for b in blocks:
+            b.close()
+            b.unlink()
+    return Batch(pat, *out)
+
+
 def mixed(count: int, start: int = 0, seed: int = DEFAULT_SEED):
     """BASELINE.json configs[2]: thirds of stance / crawl / trot, one plan per pattern."""
     third = count // 3
     sizes = {"stance": count - 2 * third, "crawl": third, "trot": third}
     return {k: generate(k, v, start, seed + i) for i, (k, v) in enumerate(sizes.items())}
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) >= 8 and sys.argv[1] == "fill":
+        _fill_shared(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6]), sys.argv[8:], int(sys.argv[7]))

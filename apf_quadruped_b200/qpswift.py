@@ -65,7 +65,8 @@ EXPORTS = [
     "QPB_BATCH_READ_STATS", "QPB_BATCH_SET_SIGMA_D", "QPB_BATCH_ENABLE_TRACE", "QPB_BATCH_READ_TRACE", "QPB_BATCH_LAST_KERNEL_MS", "QPB_BATCH_LAST_LAUNCHES", "QPB_BATCH_LAST_KERNEL",
     "QPB_LDL_NUMERIC_BATCH", "QPB_LDL_SOLVE_BATCH", "QPB_LAST_ERROR", "QPB_DEVICE_COUNT", "QPB_PLAN_CACHE_INFO",
     "QPB_BATCH_ROW_WIDTHS", "QP_SETUP_BATCH_MULTI", "QPB_BATCH_CREATE_MULTI", "QPB_MULTI_DEVICES", "QPB_MULTI_SHARD",
-    "QP_SOLVE_BATCH_MULTI", "QP_SOLVE_BATCH_MULTI_DEVICE", "QP_CLEANUP_BATCH_MULTI", "QPB_MULTI_LAST_ERROR",
+    "QP_SOLVE_BATCH_MULTI", "QP_SOLVE_BATCH_MULTI_DEVICE", "QP_CLEANUP_BATCH_MULTI", "QPB_MULTI_LAST_ERROR", "QPB_FP64_PEAK",
+    "QP_SOLVE_BATCH_DEVICE_INDEXED", "QPB_WBC_FORMULATE_DEVICE", "QPB_WBC_TORQUES_DEVICE", "QPB_WBC_DESCRIPTORS",
 ]
 
 _lib = None
@@ -155,6 +156,12 @@ def lib():
         lb.QP_SOLVE_BATCH_MULTI_DEVICE.argtypes = [V, L, C.POINTER(settings)] + [V] * 15
         lb.QP_CLEANUP_BATCH_MULTI.argtypes = [V]
         lb.QPB_MULTI_LAST_ERROR.restype = C.c_char_p
+        lb.QPB_FP64_PEAK.restype = D
+        lb.QP_SOLVE_BATCH_DEVICE_INDEXED.restype = L
+        lb.QP_SOLVE_BATCH_DEVICE_INDEXED.argtypes = [V, L, C.POINTER(settings), V, V] + [V] * 6 + [V] * 4 + [V, V, V]
+        lb.QPB_WBC_DESCRIPTORS.restype = L
+        lb.QPB_WBC_DESCRIPTORS.argtypes = [V, C.c_int, C.POINTER(C.c_uint64), L, PD]
+        lb.QPB_FP64_PEAK.argtypes = [C.c_int, C.c_int]
         lb.QPB_LAST_ERROR.restype = C.c_char_p
         lb.QPB_DEVICE_COUNT.restype = C.c_int
         _lib = lb
@@ -363,6 +370,12 @@ class BatchSolver:
                                          dz, ds, dflag, diters, dfval, dstat, stream)
         if rc < 0:
             raise RuntimeError(f"QP_SOLVE_BATCH_DEVICE failed ({rc}): {last_error()}")
+
+    def solve_device_indexed(self, rows, opts, dindex, dcount, dPpr, dApr, dGpr, dc, dh, db, dx, dy, dz, ds, dflag, diters, stream=None):
+        """``QP_SOLVE_BATCH_DEVICE_INDEXED``: the QPs listed in dindex[0 .. *dcount) (device memory)."""
+        rc = lib().QP_SOLVE_BATCH_DEVICE_INDEXED(self.handle, int(rows), C.byref(opts), dindex, dcount, dPpr, dApr, dGpr, dc, dh, db, dx, dy, dz, ds, dflag, diters, stream)
+        if rc < 0:
+            raise RuntimeError(f"QP_SOLVE_BATCH_DEVICE_INDEXED failed ({rc}): {last_error()}")
 
     def ldl_numeric_device(self, count, dvals, dzdiag, dLx, dD, stream=None):
         rc = lib().QPB_LDL_NUMERIC_BATCH(self.handle, int(count), dvals, dzdiag, dLx, dD, stream)

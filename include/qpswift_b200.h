@@ -141,6 +141,32 @@ qp_int QP_SOLVE_BATCH_DEVICE(QPBatch *batch, qp_int count, const settings *opts,
 qp_int QPB_DENSE_TO_VALUES_DEVICE(QPBatch *batch, qp_int count, int ordering, const qp_real *dP, const qp_real *dA, const qp_real *dG, qp_real *dPpr, qp_real *dApr, qp_real *dGpr, int *dviolation, void *stream);
 qp_int QP_SOLVE_BATCH_DENSE(QPBatch *batch, qp_int count, const settings *opts, int ordering, const qp_real *P, const qp_real *A, const qp_real *G, const qp_real *c, const qp_real *h, const qp_real *b, qp_real *x, qp_real *y, qp_real *z, qp_real *s, qp_int *flag, qp_int *iters, qp_int *violation);
 
+/* The QPs whose rows are listed in dindex[0 .. *dcount_ptr) -- list and count in device memory, read by the kernel,
+ * so a list compacted on the device (the robots that are in this contact pattern this tick) needs no host round trip
+ * and the launch can be captured in a CUDA graph.  `rows` = rows the arrays hold (<= capacity, < 2^24).  Rows that
+ * are not listed are not touched.  Asynchronous on `stream`. */
+qp_int QP_SOLVE_BATCH_DEVICE_INDEXED(QPBatch *batch, qp_int rows, const settings *opts, const int *dindex, const int *dcount_ptr, const qp_real *dPpr, const qp_real *dApr, const qp_real *dGpr, const qp_real *dc, const qp_real *dh, const qp_real *db, qp_real *dx, qp_real *dy, qp_real *dz, qp_real *ds, int *dflag, int *diters, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The DogBot whole-body-control QP built on the device, and the joint torques from its solution
+ * (8 f1).  What dogbot_controller formulates every tick from iDynTree's quantities (main.cpp:1471-1647 stance,
+ * 1734-1992 trot, 2943-3230 crawl) comes as ONE packed state row of QPB_WBC_STATE_DOUBLES doubles per robot:
+ *   Jc[12][6] | Jj[12][12] | Mcom[6][6] | Mjj[12][12] | bias[18] | Jdqd[12] | W[6] | q[12] | dq[12] | vdot_sw[12]
+ * (feet in the order br, bl, fl, fr; row-major blocks; W = the desired CoM wrench, main.cpp:1572; vdot_sw = the
+ * desired swing-foot accelerations, main.cpp:1991).  kind: 0 stance (4 feet), 1 trot (bl, fr), 2 crawl (bl, fl, fr);
+ * the batch's pattern must be that kind's (checked once; QPB_E_PATTERN otherwise).
+ *   QPB_WBC_FORMULATE_DEVICE  writes the plan-ordered value rows Ppr | Apr | Gpr | c | h | b of robots 0 .. count-1, or
+ *                             of the robots listed in dindex[0 .. *dcount_ptr) (both may be NULL), at the robot's row.
+ *   QPB_WBC_TORQUES_DEVICE    tau[robot][12] = Mjj qdd + bias_j - Jst_j' f from x[robot][30] (main.cpp:1667, 2023, 3246).
+ * Every number is a fixed sequence of IEEE-754 operations (apf_quadruped_b200/wbc.py restates them in numpy).
+ * ------------------------------------------------------------------------------------------- */
+#define QPB_WBC_STATE_DOUBLES 468
+qp_int QPB_WBC_FORMULATE_DEVICE(QPBatch *batch, int kind, qp_int count, const qp_real *dstate, const int *dindex, const int *dcount_ptr, qp_real *dPpr, qp_real *dApr, qp_real *dGpr, qp_real *dc, qp_real *dh, qp_real *db, void *stream);
+/* (host only) the formula table the formulation kernel walks: one descriptor per entry of Ppr | Apr | Gpr | c | h | b
+ * (op | flag << 4 | a << 8 | b << 32, csrc/wbc.cuh) and the 32 constants that follow the state row. */
+qp_int QPB_WBC_DESCRIPTORS(const QPBPlan *plan, int kind, unsigned long long *desc, qp_int capacity, qp_real *consts);
+qp_int QPB_WBC_TORQUES_DEVICE(QPBatch *batch, int kind, qp_int count, const qp_real *dstate, const qp_real *dx, qp_real *dtau, const int *dindex, const int *dcount_ptr, void *stream);
+
 void QP_CLEANUP_BATCH(QPBatch *batch);
 
 /* nnz[3] = entries of P, A, G per QP (the widths of the value rows Ppr / Apr / Gpr). */
@@ -217,6 +243,11 @@ qp_int QPB_LDL_SOLVE_BATCH(QPBatch *batch, qp_int count, const qp_real *dLx, con
 /* QP_SETUP caches the symbolic plan (and the single-QP batch) per sparsity pattern; the cache is bounded and
  * evicts the least recently used plan.  what = 0: plans cached now, 1: the cache's capacity. */
 qp_int QPB_PLAN_CACHE_INFO(int what);
+
+/* Measured FP64 peak of `device` (< 0: the current one) in TFLOP/s: 8 independent chains a <- a * b + c per thread as
+ * one DFMA (fused != 0) or as DMUL + DADD -- the form this library executes, since unfused arithmetic is part of
+ * the bit-exactness contract.  The denominator of the FP64-pipe roofline. */
+double QPB_FP64_PEAK(int device, int fused);
 
 const char *QPB_LAST_ERROR(void);
 int QPB_DEVICE_COUNT(void);

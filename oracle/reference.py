@@ -19,6 +19,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libqpswift_ref.so")
+REF_O3_SO = os.path.join(HERE, "_ref", "libqpswift_ref_O3.so")  # timing variant only (-O3 -march=x86-64-v3)
 PORT_SO = os.path.join(HERE, "liboracle_port.so")
 
 L = C.c_long
@@ -284,7 +285,7 @@ def run_batch(batch, *, kind=None, threads=None, permut="shared", sigma_d=0.0, m
     pat = batch.pattern
     cnt = batch.count
     if isinstance(permut, str):
-        if kind == "reference":
+        if kind in ("reference", "reference_O3"):
             i0 = 0
             permut = solve_sparse(pat, batch.Ppr[i0], batch.Apr[i0], batch.Gpr[i0], batch.c[i0], batch.h[i0], batch.b[i0],
                                   kind="reference", maxit=0).plan["P"]
@@ -298,7 +299,7 @@ def run_batch(batch, *, kind=None, threads=None, permut="shared", sigma_d=0.0, m
     out = {"x": np.empty((cnt, pat.n)), "y": np.empty((cnt, pat.p)), "z": np.empty((cnt, pat.m)), "s": np.empty((cnt, pat.m)),
            "flag": np.empty(cnt, dtype=np.int64), "iters": np.empty(cnt, dtype=np.int64), "fval": np.empty(cnt)}
     vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None and a.size else None
-    path = (REF_SO if kind == "reference" else PORT_SO).encode()
+    path = {"reference": REF_SO, "reference_O3": REF_O3_SO}.get(kind, PORT_SO).encode()
     threads = threads or (os.cpu_count() or 1)
     secs = _DRIVER.oracle_run_batch(
         C.c_char_p(path), C.c_int(int(threads)), C.c_long(cnt), L(pat.n), L(pat.m), L(pat.p),
@@ -310,3 +311,55 @@ def run_batch(batch, *, kind=None, threads=None, permut="shared", sigma_d=0.0, m
         raise RuntimeError("oracle driver could not load " + path.decode())
     out["threads"] = int(min(threads, max(cnt, 1)))
     return out, float(secs)
+
+
+def _driver():
+    global _DRIVER
+    if _DRIVER is None:
+        if not os.path.exists(DRIVER_SO):
+            raise FileNotFoundError(f"{DRIVER_SO} missing: run `make -C oracle driver`")
+        _DRIVER = C.CDLL(DRIVER_SO, mode=C.RTLD_LOCAL)
+        _DRIVER.oracle_run_batch.restype = D
+    _DRIVER.oracle_run_batch_dense.restype = D
+    _DRIVER.oracle_control_loop.restype = C.c_int
+    return _DRIVER
+
+
+def run_batch_dense(batch, *, lib_path=None, threads=None, reltol=None, abstol=None, outputs=True):
+    """Controller style (main.cpp:1649-1663): every instance through ``QP_SETUP_dense``
+    (dense column-major blocks: densetosparse + AMD + symbolic analysis per QP) + ``QP_SOLVE`` + ``QP_CLEANUP_dense``,
+    one instance per pinned host thread.  ``lib_path``: any library exporting qpSWIFT's C API (default: the compiled
+    reference).  Returns (dict with x, flag, iters, threads; wall seconds)."""
+    drv = _driver()
+    pat, cnt = batch.pattern, batch.count
+    P, A, G = [np.ascontiguousarray(a) for a in batch.dense_batch()]
+    vals = [P, A, G] + [np.ascontiguousarray(a, dtype=np.float64) for a in (batch.c, batch.h, batch.b)]
+    out = {"x": np.empty((cnt, pat.n)), "flag": np.empty(cnt, dtype=np.int64), "iters": np.empty(cnt, dtype=np.int64)}
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None and a.size else None
+    threads = threads or (os.cpu_count() or 1)
+    secs = drv.oracle_run_batch_dense(C.c_char_p((lib_path or REF_SO).encode()), C.c_int(int(threads)), C.c_long(cnt), L(pat.n), L(pat.m), L(pat.p),
+                                      *[vp(a) for a in vals], D(-1.0 if reltol is None else float(reltol)), D(-1.0 if abstol is None else float(abstol)),
+                                      *([vp(out[k]) for k in ("x", "flag", "iters")] if outputs else [None] * 3))
+    if secs < 0:
+        raise RuntimeError(f"oracle driver could not load {lib_path or REF_SO}")
+    out["threads"] = int(min(threads, max(cnt, 1)))
+    return out, float(secs)
+
+
+def control_loop(batch, ticks, *, lib_path=None, reltol=1e-2, abstol=1e-2, cleanup=True):
+    """``ticks`` control ticks on the calling thread, one QP each: ``QP_SETUP_dense`` -> tolerances (the controller's
+    1e-2, main.cpp:1651-1652) -> ``QP_SOLVE`` -> x -> ``QP_CLEANUP_dense``, cycling through ``batch``.  Works on the
+    compiled reference and on libqpswift_b200.so alike (same C API).  Returns per-tick microseconds etc."""
+    drv = _driver()
+    pat, cnt = batch.pattern, batch.count
+    P, A, G = [np.ascontiguousarray(a) for a in batch.dense_batch()]
+    vals = [P, A, G] + [np.ascontiguousarray(a, dtype=np.float64) for a in (batch.c, batch.h, batch.b)]
+    us, setup_us = np.empty(ticks), np.empty(ticks)
+    x, flag, iters = np.empty((ticks, pat.n)), np.empty(ticks, dtype=np.int64), np.empty(ticks, dtype=np.int64)
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None and a.size else None
+    rc = drv.oracle_control_loop(C.c_char_p((lib_path or REF_SO).encode()), C.c_long(int(ticks)), C.c_long(cnt), L(pat.n), L(pat.m), L(pat.p),
+                                 *[vp(a) for a in vals], D(float(reltol)), D(float(abstol)), C.c_int(1 if cleanup else 0),
+                                 vp(us), vp(setup_us), vp(x), vp(flag), vp(iters))
+    if rc != 0:
+        raise RuntimeError(f"oracle driver could not load {lib_path or REF_SO}")
+    return {"us": us, "setup_us": setup_us, "x": x, "flag": flag, "iters": iters}

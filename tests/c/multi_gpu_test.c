@@ -63,7 +63,7 @@ int main(int argc, char **argv)
 
 	/* the prototype: the first QP of the batch, set up as the reference's caller does */
 	QP *proto = QP_SETUP(n, m, p, Pjc, Pir, in[0], p ? Ajc : NULL, p ? Air : NULL, p ? in[1] : NULL, Gjc, Gir, in[2], in[3], in[4], p ? in[5] : NULL, 0.0, NULL);
-	if (!proto || proto->stats->Flag == QP_FATAL) { fprintf(stderr, "QP_SETUP failed\n"); return 4; }
+	if (!proto || proto->stats->Flag == QP_KKTFAIL) { fprintf(stderr, "QP_SETUP failed\n"); return 4; } /* (Flag stays QP_FATAL until QP_SOLVE, qpSWIFT.c:80) */
 
 	const size_t ow[4] = {(size_t)n, (size_t)p, (size_t)m, (size_t)m};
 	qp_real *one[4], *many[4];
