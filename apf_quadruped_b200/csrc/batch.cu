@@ -17,6 +17,7 @@
 #include "stream_gen.cuh"
 #include "warp_kernel.cuh"
 #include "wbc.cuh"
+#include "rollout.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -194,7 +195,7 @@ struct QPBatch
 	long last_launches = 0;
 	int last_kernel = 0; // 0 warp-per-QP kernel (interpreted schedules), 1 throughput kernel (one QP per thread), 2 the same, pattern-specialised, 3 warp-per-QP kernel, pattern-specialised
 	// WBC formulation on the device (wbc.cuh): descriptor tables per contact pattern kind, built on first use
-	WbcDesc *d_wbc_desc = nullptr;
+	unsigned *d_wbc_desc = nullptr;
 	double *d_wbc_consts = nullptr;
 	WbcTables wbc;
 	std::mutex lock;
@@ -807,6 +808,30 @@ qp_int QPB_BATCH_READ_TRACE(QPBatch *B, qp_int count, qp_int maxit, qp_real *tra
 	return 0;
 }
 
+// One control tick of a rollout, device side (rollout.cuh): integrate the previous tick's solutions x [robots][30]
+// (skipped while *dtick == 0), advance the contact schedule, move the swing feet, rebuild the state rows, then list the
+// robots of each contact pattern: dlists [3][robots] (stance, trot, crawl; ascending), dcounts [3]; *dtick += 1.
+// The model's constants are fixed here (and mirrored by apf_quadruped_b200/rollout.py, which steps the same model in numpy).
+qp_int QPB_ROLLOUT_TICK_DEVICE(int device, qp_int robots, qp_int first_robot, unsigned long long seed, qp_real *dstate, qp_real *drobot, const qp_real *dx, int *dkind, int *dlists, int *dcounts, long long *dtick, void *stream)
+{
+	if (robots < 1 || !dstate || !drobot || !dx || !dkind || !dlists || !dcounts || !dtick) return fail(QPB_E_ARG, "QPB_ROLLOUT_TICK_DEVICE: bad argument", cudaSuccess);
+	if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+	RolloutParams P;
+	P.dt = 0.0025;            // 400 Hz control loop (main.cpp:1107)
+	P.kp_com = 3000.0; P.kd_com = 50.0; // Kcom, Dcom (main.cpp:1498-1499)
+	P.g = 9.81; P.mass_g = 21.27 * 9.81; // robot_mass * g_acc (main.cpp:1572; dogbot.urdf)
+	P.goal_spread = 0.03; P.sat = 0.05; P.step = 0.025; P.half = 0.5; P.kpa = 1.5; // APF step planner (main.cpp:1331-1390)
+	P.kp_sw = 300.0;          // Kp of the swing-foot tracking (main.cpp:1985)
+	P.qdd_sat = 40.0; P.kq = 400.0; P.kdq = 40.0; P.a_sat = 30.0; P.replan = 0.25; // the rollout model's joint posture spring-damper and saturations (rollout.cuh)
+	P.phase_ticks = 25; P.robot_stride = 7; P.first_robot = (int)first_robot;
+	P.seed = seed;
+	cudaStream_t st = (cudaStream_t)stream;
+	rollout_tick_kernel<<<(unsigned)((robots + 127) / 128), 128, 0, st>>>(dstate, drobot, dx, dkind, dtick, (int)robots, P);
+	rollout_lists_kernel<<<1, 1024, 0, st>>>(dkind, dlists, dcounts, dtick, (int)robots);
+	CUDA_TRY(cudaGetLastError());
+	return 0;
+}
+
 // The descriptor table of `kind` for a plan's pattern (host only): desc[i] = op_a | b << 32 for every entry of the value
 // rows Ppr | Apr | Gpr | c | h | b, and the 32 constants behind the state row.  Returns the number of descriptors, or
 // QPB_E_PATTERN when the pattern is not that kind's.  Lets the tables be checked on the host (tests/test_wbc.py).
@@ -825,8 +850,10 @@ static int ensure_wbc(QPBatch *B, int kind)
 	if (B->d_wbc_desc && B->wbc.kind == kind) return 0;
 	if (B->d_wbc_desc) return fail(QPB_E_ARG, "WBC: this batch's pattern was bound to another contact pattern kind", cudaSuccess);
 	if (kind < 0 || kind > 2 || !wbc_build_tables(B->wbc, kind, B->plan)) { B->wbc.kind = -1; return fail(QPB_E_PATTERN, "WBC: the batch's sparsity pattern is not the DogBot pattern of that kind (0 stance, 1 trot, 2 crawl)", cudaSuccess); }
-	CUDA_TRY(cudaMalloc(&B->d_wbc_desc, B->wbc.desc.size() * sizeof(WbcDesc)));
-	CUDA_TRY(cudaMemcpy(B->d_wbc_desc, B->wbc.desc.data(), B->wbc.desc.size() * sizeof(WbcDesc), cudaMemcpyHostToDevice));
+	std::vector<uint32_t> packed(B->wbc.desc.size());
+	for (size_t i = 0; i < packed.size(); ++i) packed[i] = wbc_pack(B->wbc.desc[i]);
+	CUDA_TRY(cudaMalloc(&B->d_wbc_desc, packed.size() * sizeof(uint32_t)));
+	CUDA_TRY(cudaMemcpy(B->d_wbc_desc, packed.data(), packed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 	CUDA_TRY(cudaMalloc(&B->d_wbc_consts, sizeof(B->wbc.consts)));
 	CUDA_TRY(cudaMemcpy(B->d_wbc_consts, B->wbc.consts, sizeof(B->wbc.consts), cudaMemcpyHostToDevice));
 	return 0;
@@ -844,7 +871,7 @@ qp_int QPB_WBC_FORMULATE_DEVICE(QPBatch *B, int kind, qp_int count, const qp_rea
 	out.Ppr = dPpr; out.Apr = dApr; out.Gpr = dGpr; out.c = dc; out.h = dh; out.b = db;
 	out.nnzP = (int)pl.nnzP; out.nnzA = (int)pl.nnzA; out.nnzG = (int)pl.nnzG; out.n = (int)pl.n; out.m = (int)pl.m; out.p = (int)pl.p;
 	const int warps = 8;
-	const long grid = std::min<long>((count + warps - 1) / warps, (long)B->sm_count * 6);
+	const long grid = std::min<long>((count + warps - 1) / warps, (long)B->sm_count * 7);
 	wbc_formulate_kernel<<<(unsigned)grid, warps * 32, warps * WBC_SMEM * sizeof(double), (cudaStream_t)stream>>>(dstate, B->d_wbc_desc, B->d_wbc_consts, out, dindex, dcount_ptr, (int)count);
 	CUDA_TRY(cudaGetLastError());
 	return 0;

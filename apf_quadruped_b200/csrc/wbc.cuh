@@ -52,6 +52,9 @@ struct WbcTables
 	double consts[WBC_SMEM - WBC_STATE];
 };
 
+// the device's form: op [0,3) | flag [3] | a [4,14) | b [14,24)  (every index is below WBC_SMEM = 500 < 1024)
+inline uint32_t wbc_pack(const WbcDesc &d) { return (d.op_a & 15u) | (((d.op_a >> 4) & 1u) << 3) | ((d.op_a >> 8) << 4) | (d.b << 14); }
+
 inline WbcDesc wbc_desc(int op, int flag, int a, int b = 0) { return WbcDesc{(uint32_t)op | ((uint32_t)flag << 4) | ((uint32_t)a << 8), (uint32_t)b}; }
 
 // The dense entry (r, c) of Q / A / G and the entries of c / h / b as formulas of the state row.  Returns false for an
@@ -194,12 +197,11 @@ struct WbcOut
 	int nnzP, nnzA, nnzG, n, m, p;
 };
 
-__device__ __forceinline__ double wbc_eval(const WbcDesc d, const double *S)
+// The rare formulas (the 6-term dot products of the cost, the limits): out of the copy path's way.
+__device__ __noinline__ double wbc_eval_formula(const unsigned op, const unsigned flag, const unsigned a, const unsigned b, const double *S)
 {
-	const unsigned op = d.op_a & 15u, flag = (d.op_a >> 4) & 1u, a = d.op_a >> 8, b = d.b;
 	double v;
 	switch (op) {
-	case WOP_COPY: v = S[a]; return flag ? -v : v;
 	case WOP_QDOT: { // (diagonal ? 1 : 0) + 50 (Jc_i . Jc_j), the sum from 0.0 in ascending k
 		double acc = 0.0;
 #pragma unroll
@@ -218,9 +220,18 @@ __device__ __forceinline__ double wbc_eval(const WbcDesc d, const double *S)
 	}
 }
 
+// Nine entries in ten are (signed) copies of a state entry or a constant: one shared-memory load and a sign flip.
+__device__ __forceinline__ double wbc_eval(const unsigned d, const double *S)
+{
+	const unsigned op = d & 7u, flag = (d >> 3) & 1u, a = (d >> 4) & 1023u;
+	if (op != WOP_COPY) return wbc_eval_formula(op, flag, a, (d >> 14) & 1023u, S);
+	const double v = S[a];
+	return flag ? -v : v;
+}
+
 // One warp per robot at a time, grid-stride over the robots (or over the list `index[0 .. *count_ptr)`).  Rows are
 // written at the robot's own index.
-__global__ void __launch_bounds__(256) wbc_formulate_kernel(const double *__restrict__ state, const WbcDesc *__restrict__ desc, const double *__restrict__ consts, const WbcOut out, const int *__restrict__ index, const int *__restrict__ count_ptr, const int count)
+__global__ void __launch_bounds__(256) wbc_formulate_kernel(const double *__restrict__ state, const unsigned *__restrict__ desc, const double *__restrict__ consts, const WbcOut out, const int *__restrict__ index, const int *__restrict__ count_ptr, const int count)
 {
 	extern __shared__ __align__(16) double wsm[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
@@ -239,7 +250,7 @@ __global__ void __launch_bounds__(256) wbc_formulate_kernel(const double *__rest
 				double v[4];
 #pragma unroll
 				for (int j = 0; j < 4; ++j)
-					if (e0 + 32 * j < len) v[j] = wbc_eval(desc[base + e0 + 32 * j], S);
+					if (e0 + 32 * j < len) v[j] = wbc_eval(__ldg(desc + base + e0 + 32 * j), S);
 #pragma unroll
 				for (int j = 0; j < 4; ++j)
 					if (e0 + 32 * j < len) __stcs(row + e0 + 32 * j, v[j]);

@@ -66,7 +66,7 @@ EXPORTS = [
     "QPB_LDL_NUMERIC_BATCH", "QPB_LDL_SOLVE_BATCH", "QPB_LAST_ERROR", "QPB_DEVICE_COUNT", "QPB_PLAN_CACHE_INFO",
     "QPB_BATCH_ROW_WIDTHS", "QP_SETUP_BATCH_MULTI", "QPB_BATCH_CREATE_MULTI", "QPB_MULTI_DEVICES", "QPB_MULTI_SHARD",
     "QP_SOLVE_BATCH_MULTI", "QP_SOLVE_BATCH_MULTI_DEVICE", "QP_CLEANUP_BATCH_MULTI", "QPB_MULTI_LAST_ERROR", "QPB_FP64_PEAK",
-    "QP_SOLVE_BATCH_DEVICE_INDEXED", "QPB_WBC_FORMULATE_DEVICE", "QPB_WBC_TORQUES_DEVICE", "QPB_WBC_DESCRIPTORS",
+    "QP_SOLVE_BATCH_DEVICE_INDEXED", "QPB_WBC_FORMULATE_DEVICE", "QPB_WBC_TORQUES_DEVICE", "QPB_WBC_DESCRIPTORS", "QPB_ROLLOUT_TICK_DEVICE",
 ]
 
 _lib = None
@@ -159,6 +159,8 @@ def lib():
         lb.QPB_FP64_PEAK.restype = D
         lb.QP_SOLVE_BATCH_DEVICE_INDEXED.restype = L
         lb.QP_SOLVE_BATCH_DEVICE_INDEXED.argtypes = [V, L, C.POINTER(settings), V, V] + [V] * 6 + [V] * 4 + [V, V, V]
+        lb.QPB_ROLLOUT_TICK_DEVICE.restype = L
+        lb.QPB_ROLLOUT_TICK_DEVICE.argtypes = [C.c_int, L, L, C.c_uint64] + [V] * 8
         lb.QPB_WBC_DESCRIPTORS.restype = L
         lb.QPB_WBC_DESCRIPTORS.argtypes = [V, C.c_int, C.POINTER(C.c_uint64), L, PD]
         lb.QPB_FP64_PEAK.argtypes = [C.c_int, C.c_int]

@@ -620,6 +620,30 @@ def main():
             gbs = nbytes * B / (kms * 1e-3) / 1e9
             assert all(torch.equal(r, d) for r, d in zip(rows_out, (devin["Ppr"], devin["Apr"], devin["Gpr"]))) and not bool(viol.any())
             kernels["dense_gather_kernel"] = {"ms": kms, "qps": B, "bytes_per_qp": nbytes, "achieved": gbs, "frac": gbs / peak, "per_s": B / (kms * 1e-3)}
+            # WBC formulation on the device: packed robot states -> plan-ordered value rows | c | h | b.  Bytes:
+            # the state row read, every value written once.
+            from apf_quadruped_b200 import wbc
+            if args.kind in wbc.KINDS:
+                states = torch.from_numpy(wbc.random_states(B)).to(dev)
+                wr = [torch.empty((B, w), dtype=torch.float64, device=dev) for w in (pat.nnzP, pat.nnzA, pat.nnzG, pat.n, pat.m, pat.p)]
+                form = wbc.Formulator(solver, args.kind)
+                fn = lambda: form.formulate(B, states.data_ptr(), *[t.data_ptr() for t in wr], stream=st)
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k0.record()
+                for _ in range(args.steps):
+                    fn()
+                k1.record()
+                torch.cuda.synchronize()
+                kms = k0.elapsed_time(k1) / args.steps
+                nbytes = 8 * (wbc.STATE + pat.nnzP + pat.nnzA + pat.nnzG + pat.n + pat.m + pat.p)
+                gbs = nbytes * B / (kms * 1e-3) / 1e9
+                ref_rows = wbc.value_rows(args.kind, states[:256].cpu().numpy())
+                assert all(np.array_equal(t[:256].cpu().numpy(), getattr(ref_rows, k)) for t, k in zip(wr, ("Ppr", "Apr", "Gpr", "c", "h", "b"))), "formulation kernel differs from the numpy restatement"
+                kernels["wbc_formulate_kernel"] = {"ms": kms, "qps": B, "bytes_per_qp": nbytes, "achieved": gbs, "frac": gbs / peak, "per_s": B / (kms * 1e-3)}
+                del states, wr
             del dense, rows_out, vals, Lx, Dd, rhs, sol
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -167,6 +167,20 @@ qp_int QPB_WBC_FORMULATE_DEVICE(QPBatch *batch, int kind, qp_int count, const qp
 qp_int QPB_WBC_DESCRIPTORS(const QPBPlan *plan, int kind, unsigned long long *desc, qp_int capacity, qp_real *consts);
 qp_int QPB_WBC_TORQUES_DEVICE(QPBatch *batch, int kind, qp_int count, const qp_real *dstate, const qp_real *dx, qp_real *dtau, const int *dindex, const int *dcount_ptr, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Rollout (BASELINE.json configs[3]): the device side of one control tick for `robots` robots whose
+ * state rows (QPB_WBC_STATE_DOUBLES each) and rollout rows (QPB_ROLLOUT_ROW_DOUBLES each: r[4][3] | goal[4][2] | dx[6] |
+ * dv[6] | noise[72]) live in device memory.  Integrates the previous tick's solutions dx [robots][30] (not on tick 0),
+ * advances the contact schedule (stance / trot / stance / crawl, 25 ticks each, staggered over the robots), draws
+ * perturbed footholds for the swing feet (counter-based, reproducible), moves the swing feet along the attractive
+ * potential field (the model of main.cpp:1261-1421), rebuilds Jc, W, q, dq, vdot_sw of every state row, and writes
+ * dkind [robots], the ascending robot lists dlists [3][robots] with dcounts [3] for the three contact patterns, and
+ * *dtick += 1.  Follow with QPB_WBC_FORMULATE_DEVICE / QP_SOLVE_BATCH_DEVICE_INDEXED / QPB_WBC_TORQUES_DEVICE per pattern on
+ * its list.  No host round trip: a tick can be captured in a CUDA graph and replayed.  first_robot: the index of robot 0
+ * in a rollout that is split over several GPUs (schedule and random draws follow the global index). */
+#define QPB_ROLLOUT_ROW_DOUBLES 104
+qp_int QPB_ROLLOUT_TICK_DEVICE(int device, qp_int robots, qp_int first_robot, unsigned long long seed, qp_real *dstate, qp_real *drobot, const qp_real *dx, int *dkind, int *dlists, int *dcounts, long long *dtick, void *stream);
+
 void QP_CLEANUP_BATCH(QPBatch *batch);
 
 /* nnz[3] = entries of P, A, G per QP (the widths of the value rows Ppr / Apr / Gpr). */
