@@ -194,6 +194,12 @@ struct QPBatch
 	double last_kernel_ms = 0.0;
 	long last_launches = 0;
 	int last_kernel = 0; // 0 warp-per-QP kernel (interpreted schedules), 1 throughput kernel (one QP per thread), 2 the same, pattern-specialised, 3 warp-per-QP kernel, pattern-specialised
+	// batch of ONE (QP_SOLVE's path, the controller's 400 Hz call): inputs, outputs, statistics and the per-iteration trace
+	// packed into one device block with a page-locked mirror, so that a solve is one upload, one launch, one download
+	double *d_single = nullptr, *h_single = nullptr;
+	size_t single_in = 0, single_total = 0; // doubles: inputs; inputs + outputs + fval + stat[8] + (flag, iters) + trace
+	long single_trace_rows = -1;
+	bool single_valid = false;              // h_single holds the results of the last solve
 	// WBC formulation on the device (wbc.cuh): descriptor tables per contact pattern kind, built on first use
 	unsigned *d_wbc_desc = nullptr;
 	double *d_wbc_consts = nullptr;
@@ -561,6 +567,8 @@ void QP_CLEANUP_BATCH(QPBatch *B)
 	cudaFree(B->d_spill_sigma);
 	for (int k = 0; k < 3; ++k) { cudaFree(B->d_dense_map[k]); cudaFree(B->d_dense[k]); }
 	cudaFree(B->d_violation);
+	cudaFree(B->d_single);
+	if (B->h_single) cudaFreeHost(B->h_single);
 	cudaFree(B->d_wbc_desc);
 	cudaFree(B->d_wbc_consts);
 	cudaFree(B->d_workspace);
@@ -631,9 +639,74 @@ qp_int QP_SOLVE_BATCH(QPBatch *B, qp_int count, const settings *opts, const qp_r
 } // extern "C"
 
 // Host-pointer solve.  Ppr == nullptr: the value rows P|A|G are in the staging buffers already (dense front-end).
+// One QP through a batch of capacity one (QP_SOLVE; the controller calls it every 2.5 ms, main.cpp:1649-1663): the
+// value row goes up in ONE copy from a page-locked block, and x, y, z, s, the objective, the statistics, flag,
+// iteration count and the per-iteration trace come back in ONE copy -- eight driver calls per solve instead of two dozen.
+static qp_int qp_solve_single(QPBatch *B, const settings *opts, const qp_real *Ppr, const qp_real *Apr, const qp_real *Gpr, const qp_real *c, const qp_real *h, const qp_real *b, qp_real *x, qp_real *y, qp_real *z, qp_real *s, qp_int *flag, qp_int *iters)
+{
+	std::lock_guard<std::mutex> guard(B->lock);
+	CUDA_TRY(cudaSetDevice(B->device));
+	const Plan &pl = B->plan;
+	const size_t w[6] = {(size_t)pl.nnzP, (size_t)pl.nnzA, (size_t)pl.nnzG, (size_t)pl.n, (size_t)pl.m, (size_t)pl.p};
+	const long rows = B->trace_on ? (long)opts->maxit + 2 : 0;
+	if (!B->d_single || rows != B->single_trace_rows) {
+		cudaFree(B->d_single);
+		if (B->h_single) cudaFreeHost(B->h_single);
+		B->d_single = B->h_single = nullptr;
+		size_t in = 0;
+		for (int i = 0; i < 6; ++i) in += (w[i] + 1) & ~(size_t)1; // (every array starts on 16 bytes: warp_copy_in's fast path)
+		B->single_in = in;
+		B->single_total = in + (((size_t)pl.n + 1) & ~(size_t)1) + (((size_t)pl.p + 1) & ~(size_t)1) + 2 * (((size_t)pl.m + 1) & ~(size_t)1) + 2 + 8 + 2 + (size_t)rows * 8;
+		CUDA_TRY(cudaMalloc(&B->d_single, B->single_total * sizeof(double)));
+		CUDA_TRY(cudaMallocHost(&B->h_single, B->single_total * sizeof(double)));
+		B->single_trace_rows = rows;
+	}
+	B->single_valid = false;
+	const qp_real *src[6] = {Ppr, Apr, Gpr, c, h, b};
+	double *din[6];
+	size_t at = 0;
+	for (int i = 0; i < 6; ++i) {
+		din[i] = B->d_single + at;
+		if (w[i]) memcpy(B->h_single + at, src[i], w[i] * sizeof(double));
+		at += (w[i] + 1) & ~(size_t)1;
+	}
+	BatchIO io;
+	io.Ppr = din[0]; io.Apr = din[1]; io.Gpr = din[2]; io.c = din[3]; io.h = din[4]; io.b = din[5];
+	const size_t ox = at, oy = ox + (((size_t)pl.n + 1) & ~(size_t)1), oz = oy + (((size_t)pl.p + 1) & ~(size_t)1), os = oz + (((size_t)pl.m + 1) & ~(size_t)1);
+	const size_t ofval = os + (((size_t)pl.m + 1) & ~(size_t)1), ostat = ofval + 2, oint = ostat + 8, otrace = oint + 2;
+	io.x = B->d_single + ox; io.y = B->d_single + oy; io.z = B->d_single + oz; io.s = B->d_single + os;
+	io.fval = B->d_single + ofval; io.stat = B->d_single + ostat;
+	io.flag = reinterpret_cast<int *>(B->d_single + oint); io.iters = io.flag + 2;
+	io.count = 1;
+	io.ready = nullptr;
+	io.trace = rows ? B->d_single + otrace : nullptr; // (only the rows of iterations that ran are read back, and those are written whole)
+	cudaStream_t st = B->stream;
+	CUDA_TRY(cudaMemcpyAsync(B->d_single, B->h_single, B->single_in * sizeof(double), cudaMemcpyHostToDevice, st));
+	CUDA_TRY(cudaEventRecord(B->ev0, st));
+	const int rc = launch_fused(B, io, opts, st);
+	if (rc) return rc;
+	CUDA_TRY(cudaEventRecord(B->ev1, st));
+	CUDA_TRY(cudaMemcpyAsync(B->h_single + B->single_in, B->d_single + B->single_in, (B->single_total - B->single_in) * sizeof(double), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	float ms = 0.f;
+	CUDA_TRY(cudaEventElapsedTime(&ms, B->ev0, B->ev1));
+	B->last_kernel_ms = ms;
+	if (x) memcpy(x, B->h_single + ox, pl.n * sizeof(double));
+	if (y && pl.p) memcpy(y, B->h_single + oy, pl.p * sizeof(double));
+	if (z) memcpy(z, B->h_single + oz, pl.m * sizeof(double));
+	if (s) memcpy(s, B->h_single + os, pl.m * sizeof(double));
+	const int *ints = reinterpret_cast<const int *>(B->h_single + oint);
+	if (flag) flag[0] = ints[0];
+	if (iters) iters[0] = ints[2];
+	B->single_valid = true;
+	return ints[0] != QP_OPTIMAL ? 1 : 0;
+}
+
 static qp_int qp_solve_batch_host(QPBatch *B, qp_int count, const settings *opts, const qp_real *Ppr, const qp_real *Apr, const qp_real *Gpr, const qp_real *c, const qp_real *h, const qp_real *b, qp_real *x, qp_real *y, qp_real *z, qp_real *s, qp_int *flag, qp_int *iters)
 {
 	if (count == 0) return 0;
+	if (count == 1 && B->capacity == 1 && Ppr && !getenv("QPB_NO_SINGLE_PATH")) return qp_solve_single(B, opts, Ppr, Apr, Gpr, c, h, b, x, y, z, s, flag, iters);
+	B->single_valid = false;
 	std::lock_guard<std::mutex> guard(B->lock);
 	CUDA_TRY(cudaSetDevice(B->device));
 	int rc = batch_alloc_staging(B);
@@ -802,6 +875,10 @@ qp_int QPB_BATCH_ENABLE_TRACE(QPBatch *B, int on)
 
 qp_int QPB_BATCH_READ_TRACE(QPBatch *B, qp_int count, qp_int maxit, qp_real *trace)
 {
+	if (B && trace && B->single_valid && count == 1 && maxit + 2 == B->single_trace_rows) { // (the single-QP path brought it back with the results)
+		memcpy(trace, B->h_single + (B->single_total - (size_t)B->single_trace_rows * 8), (size_t)B->single_trace_rows * 8 * sizeof(double));
+		return 0;
+	}
 	if (!B || !trace || !B->d_trace || count < 0 || count > B->capacity || maxit + 2 != B->trace_rows) return fail(QPB_E_ARG, "QPB_BATCH_READ_TRACE: no trace of that shape", cudaSuccess);
 	CUDA_TRY(cudaSetDevice(B->device));
 	CUDA_TRY(cudaMemcpy(trace, B->d_trace, (size_t)count * B->trace_rows * 8 * sizeof(double), cudaMemcpyDeviceToHost));
@@ -942,6 +1019,12 @@ qp_int QPB_GENERATED_KERNELS(unsigned long long *keys, int capacity) { return li
 // Host access to fval / stat of the last host-pointer solve (used by QP_SOLVE to fill `stats`).
 qp_int QPB_BATCH_READ_STATS(QPBatch *B, qp_int count, qp_real *fval, qp_real *stat)
 {
+	if (B && B->single_valid && count == 1) {
+		const double *st = B->h_single + (B->single_total - (size_t)B->single_trace_rows * 8 - 12); // fval(2) | stat[8] | flag, iters
+		if (fval) fval[0] = st[0];
+		if (stat) memcpy(stat, st + 2, 8 * sizeof(double));
+		return 0;
+	}
 	if (!B || !B->d_fval) return fail(QPB_E_ARG, "QPB_BATCH_READ_STATS: nothing solved yet", cudaSuccess);
 	if (count < 0 || count > B->capacity) return fail(QPB_E_ARG, "QPB_BATCH_READ_STATS: count > capacity", cudaSuccess);
 	CUDA_TRY(cudaSetDevice(B->device));

@@ -234,11 +234,29 @@ def latency_leg(qpswift, dogbot, ticks=1000):
     return out
 
 
+class QuietStdout:
+    """NCCL prints its version banner (and, at INFO, everything else) on the C-level stdout; this run's stdout carries
+    exactly one JSON line.  While active, file descriptor 1 points at `path`; restore() puts the real stdout back."""
+
+    def __init__(self, path):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_APPEND, 0o644)
+        os.dup2(fd, 1)
+        os.close(fd)
+
+    def restore(self):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def nccl_logging(rank):
-    """NCCL's own evidence of the communicator (ranks, transports) goes to a file next to the other records, so
-    that stdout stays one JSON line.  A caller who has set NCCL_DEBUG keeps whatever they asked for."""
-    if os.environ.get("NCCL_DEBUG"):
-        return os.environ.get("NCCL_DEBUG_FILE")
+    """NCCL's own evidence of the communicator (ranks, transports) goes to files next to the other records.  A caller
+    who has asked for NCCL_DEBUG=INFO / TRACE themselves keeps exactly what they asked for (on their stdout).
+    Returns (log file pattern or None, QuietStdout or None)."""
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("INFO", "TRACE"):
+        return os.environ.get("NCCL_DEBUG_FILE"), None
     out = os.path.join(ROOT, "gpurun_out")
     try:
         os.makedirs(out, exist_ok=True)
@@ -247,7 +265,7 @@ def nccl_logging(rank):
     os.environ["NCCL_DEBUG"] = "INFO"
     os.environ["NCCL_DEBUG_SUBSYS"] = "INIT,ENV"
     os.environ["NCCL_DEBUG_FILE"] = os.path.join(out, "nccl_bench_%h_%p.log")
-    return os.environ["NCCL_DEBUG_FILE"]
+    return os.environ["NCCL_DEBUG_FILE"], QuietStdout(os.path.join(out, f"nccl_bench_stdout_rank{rank}.log"))
 
 
 def nccl_summary(pattern, world):
@@ -514,10 +532,10 @@ def main():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    nccl_log = None
+    nccl_log = quiet = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        nccl_log = nccl_logging(rank)
+        nccl_log, quiet = nccl_logging(rank)
         dist.init_process_group("nccl", device_id=dev)
     env = (rank, world, local, dev)
 
@@ -688,10 +706,13 @@ def main():
                 line["cpu_baseline_extras"] = cpu_extras(batch)
             except Exception as e:
                 line["cpu_baseline_extras"] = {"error": repr(e)}
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if quiet is not None:
+        quiet.restore()
+    if rank == 0:
+        print(json.dumps(line), flush=True)  # (the last thing on stdout, after NCCL has said all it has to say)
 
 
 if __name__ == "__main__":
