@@ -133,6 +133,22 @@ class IR:
         self.emit(kind, v, *a)
         return v
 
+    def gather2(self, st, offsets):
+        """gather() of KKT entries that may lie in the value row (global scratch) AND in shared memory (the (z,z)
+        diagonal): one load per address space, each padded with its own zero, joined by a lane mask."""
+        inv = [st.in_v(o) for o in offsets]
+        has_v = any(inv)
+        has_s = any(o is not None and not v for o, v in zip(offsets, inv))
+        if not has_v:
+            return self.gather(offsets, st.ZERO)
+        if not has_s:
+            return self.gather(offsets, st.VZERO)
+        gv = self.gather([o if v else None for o, v in zip(offsets, inv)], st.VZERO)
+        gs = self.gather([None if v else o for o, v in zip(offsets, inv)], st.ZERO)
+        p = self.p()
+        self.emit("pmask", p, sum(1 << l for l, v in enumerate(inv) if v))
+        return self.op("sel", p, gv, gs)
+
     def chain(self, acc, terms_per_lane, fill):
         """acc -= S[a_t] * S[b_t] for t = 0, 1, ... per lane: terms_per_lane[l] is lane l's list of (a, b) byte
         offsets; shorter lists are padded with the constant +0.0 (acc - (+0)(+0) leaves every acc unchanged).
@@ -263,6 +279,8 @@ class Emulator:
                     env[st[1]] = env[st[2]] != st[3]
                 elif k == "prange":
                     env[st[1]] = (L >= st[2]) & (L <= st[3])
+                elif k == "pmask":
+                    env[st[1]] = ((st[2] >> L) & 1).astype(bool)
                 else:
                     raise ValueError(k)
         return S
@@ -275,10 +293,16 @@ class Emulator:
 LAYOUT_FIELDS = ["zero", "V", "c", "h", "b", "zd", "Lx", "D", "T", "rhs", "x", "y", "z", "s", "r", "lam", "ds", "dz", "dsl", "total", "tsize"]
 
 
-def compact_layout(n, m, p, N, nV, lnz):
+def compact_layout(n, m, p, N, nV, lnz, vglobal=True):
     """SliceLayout (csrc/program.h) with the scratch area T cut down to what the generated programs use: the
     permuted work vector of the solves (N) and the products of one column of the backward sweep (64); the
-    kernel's own scratch (-(P x): n, rho's products: 2m) fits in the same doubles."""
+    kernel's own scratch (-(P x): n, rho's products: 2m) fits in the same doubles.
+
+    vglobal: the value row V = P | A | G (read-only during a solve, a third of the slice) is NOT kept in shared
+    memory: it lies in the warp's scratch row in global memory (L2-resident; written once per QP with the v + 0.0
+    normalisation), followed by a zero.  The programs keep ONE address space -- a double of the slice is in shared
+    memory below `smem`, in the scratch row from `V` on -- so the host emulator is unchanged; only the printed CUDA
+    distinguishes the two (print_function).  `total` covers both, `smem` is what a warp occupies on chip."""
     even = lambda v: (v + 1) & ~1
     lay, at = {}, 0
 
@@ -288,24 +312,32 @@ def compact_layout(n, m, p, N, nV, lnz):
         at += even(count)
 
     take("zero", 2)
-    for name, cnt in (("V", nV), ("c", n), ("h", m), ("b", p), ("zd", m), ("Lx", lnz), ("D", N)):
+    head = (("V", nV),) if not vglobal else ()
+    for name, cnt in head + (("c", n), ("h", m), ("b", p), ("zd", m), ("Lx", lnz), ("D", N)):
         take(name, cnt)
     lay["tsize"] = max(even(N) + 64, even(2 * m), even(n))
     take("T", lay["tsize"])
     for name, cnt in (("rhs", N), ("x", n), ("y", p), ("z", m), ("s", m), ("r", N), ("lam", max(m, n)), ("ds", m), ("dz", m), ("dsl", m)):
         take(name, cnt)
+    lay["smem"] = at
+    if vglobal:
+        take("V", nV)
+        take("vzero", 2)
+    else:
+        lay["vzero"] = lay["zero"]
     lay["total"] = at
+    lay["vglobal"] = bool(vglobal)
     return lay
 
 
 class Structure:
-    def __init__(self, plan):
+    def __init__(self, plan, vglobal=True):
         info = plan.stream_info()
         assert info["ok"] == 1
         sl = info["layout"]
         self.N = N = plan.info("N")
         pat0 = plan.pattern
-        self.lay = compact_layout(pat0.n, pat0.m, pat0.p, N, len(pat0.Pir) + len(pat0.Air) + len(pat0.Gir), plan.info("lnz"))
+        self.lay = compact_layout(pat0.n, pat0.m, pat0.p, N, len(pat0.Pir) + len(pat0.Air) + len(pat0.Gir), plan.info("lnz"), vglobal)
         lay = self.lay
         self.Lp = [int(v) for v in plan.array("Lp")]
         self.Li = [int(v) for v in plan.array("Li")]
@@ -317,6 +349,8 @@ class Structure:
         self.n, self.m, self.p = pat.n, pat.m, pat.p
         nV = len(pat.Pir) + len(pat.Air) + len(pat.Gir)
         self.ZERO = lay["zero"] * 8
+        self.VZERO = lay["vzero"] * 8          # the zero of the value row's address space
+        self.VBYTE = lay["V"] * 8 if lay["vglobal"] else None
 
         def slice_offset(e):
             """stream-layout element -> byte offset in the warp kernel's slice (None: the constant +0.0)"""
@@ -356,6 +390,10 @@ class Structure:
 
     def col(self, j):
         return [(self.Li[q], q) for q in range(self.Lp[j], self.Lp[j + 1])]
+
+    def in_v(self, off):
+        """Is the byte offset in the value row's address space (global scratch row) rather than in shared memory?"""
+        return self.VBYTE is not None and off is not None and off >= self.VBYTE
 
     def Lx(self, q):
         return (self.lay["Lx"] + q) * 8
@@ -427,7 +465,7 @@ def gen_factor(st: Structure, passes=None) -> IR:
     # ---- leaf pivots: D[i] = regularise(0 + K(i,i))  (ldl.c:284, 299, 319-320) -----------------------
     for w in range(0, len(st.leaf), NLANE):
         chunk = st.leaf[w:w + NLANE]
-        v = ir.gather([st.kdiag[i] for i in chunk], ZERO)
+        v = ir.gather2(st, [st.kdiag[i] for i in chunk])
         v = ir.op("regu", v)
         ir.scatter([st.D(i) for i in chunk], v)
     ir.emit("sync")
@@ -437,7 +475,7 @@ def gen_factor(st: Structure, passes=None) -> IR:
         chunk = ent[w:w + NLANE]
         for q, k, i in chunk:
             assert st.kinit[(k, i)] is not None, "entry of a leaf column without a KKT entry"
-        y = ir.gather([st.kinit[(k, i)] for q, k, i in chunk], ZERO)
+        y = ir.gather2(st, [st.kinit[(k, i)] for q, k, i in chunk])
         dv = ir.gather([st.D(i) for q, k, i in chunk], st.D(chunk[0][2]))
         l = ir.op("div", y, dv)
         ir.scatter([st.Lx(q) for q, k, i in chunk], l)
@@ -452,7 +490,7 @@ def gen_factor(st: Structure, passes=None) -> IR:
         if order is None:
             raise ValueError("the rows' Pattern orders have no common extension")
         inpat = {k: set(st.pat[k]) for k in rows}
-        d = ir.gather([st.kdiag[k] for k in rows], ZERO)
+        d = ir.gather2(st, [st.kdiag[k] for k in rows])
         Y, published = {}, set()
 
         def work(j):
@@ -462,13 +500,13 @@ def gen_factor(st: Structure, passes=None) -> IR:
                     v = ir.d()
                     ir.emit("const", v, 0.0)
                 else:
-                    v = ir.gather(offs, ZERO)
+                    v = ir.gather2(st, offs)
                 Y[j] = v
             return Y[j]
 
         for i in order:
             if st.is_leaf[i]:
-                y = ir.gather([st.kinit[(k, i)] if i in inpat[k] else None for k in rows], ZERO)
+                y = ir.gather2(st, [st.kinit[(k, i)] if i in inpat[k] else None for k in rows])
                 l = ir.gather([st.Lx(st.colpos[(k, i)]) if i in inpat[k] else None for k in rows], ZERO)
                 d = ir.op("msub", d, l, y)  # D[k] -= l*y  (ldl.c:306)
             else:
@@ -500,7 +538,7 @@ def gen_factor(st: Structure, passes=None) -> IR:
             dr = ir.op("regu", d)
             ir.scatter([st.D(k) if k in left else None for k in rows], dr)
         ir.emit("sync")
-    return ir
+    return hoist_v_loads(ir, st)
 
 
 def gen_solve(st: Structure, passes=None) -> IR:
@@ -678,11 +716,23 @@ def gen_resid(st: Structure) -> IR:
     tmp = lay["T"]  # scratch: -(P x), read by the kernel's sums
     zero = ir.d()
     ir.emit("const", zero, 0.0)
+
+    def chain(acc, terms_per_lane):
+        """acc -= V[a_t] * S[b_t], t ascending, per lane.  Value row in shared memory: one table-driven loop.  Value row
+        in global memory: unrolled, so that the loads of V can be issued far ahead of their use (hoist_v_loads)."""
+        if not st.lay["vglobal"]:
+            return ir.chain(acc, terms_per_lane, ZERO)
+        for t in range(max((len(tl) for tl in terms_per_lane), default=0)):
+            a = ir.gather([tl[t][0] if t < len(tl) else None for tl in terms_per_lane], st.VZERO)
+            b = ir.gather([tl[t][1] if t < len(tl) else None for tl in terms_per_lane], ZERO)
+            acc = ir.op("msub", acc, a, b)  # (a padded term is acc - (+0)(+0): no accumulator here is ever -0.0)
+        return acc
+
     for w0 in range(0, n, NLANE):
         rows = list(range(w0, min(n, w0 + NLANE)))
-        acc = ir.chain(zero, [Px[i] for i in rows], ZERO)
+        acc = chain(zero, [Px[i] for i in rows])
         ir.scatter([(tmp + i) * 8 for i in rows], acc)
-        acc = ir.chain(acc, [Gtz[i] + Aty[i] for i in rows], ZERO)
+        acc = chain(acc, [Gtz[i] + Aty[i] for i in rows])
         cv = ir.gather([B("c", i) for i in rows], ZERO)
         acc = ir.op("add", acc, ir.op("mulc", cv, -1.0))  # rx[i] += c[i] * (-1)
         ir.scatter([B("r", i) for i in rows], acc)
@@ -690,12 +740,42 @@ def gen_resid(st: Structure) -> IR:
     outs = [(Ax[i], B("b", i), None, B("r", n + i)) for i in range(p)] + [(Gx[i], B("h", i), B("s", i), B("r", n + p + i)) for i in range(m)]
     for w0 in range(0, len(outs), NLANE):
         chunk = outs[w0:w0 + NLANE]
-        acc = ir.chain(zero, [o[0] for o in chunk], ZERO)
+        acc = chain(zero, [o[0] for o in chunk])
         u = ir.gather([o[1] for o in chunk], ZERO)
         v = ir.gather([o[2] for o in chunk], ZERO)
         acc = ir.op("add", acc, ir.op("sub", u, v))
         ir.scatter([o[3] for o in chunk], acc)
     ir.emit("sync")
+    return hoist_v_loads(ir, st)
+
+
+def hoist_v_loads(ir: IR, st: Structure, dist=120):
+    """Value-row loads (global memory, an L2 round trip each) are moved `dist` statements ahead of where the program
+    needs them -- together with the table load that feeds them -- so that they are in flight while the warp works on
+    shared memory.  Legal anywhere: the value row is read-only while the programs run.  Marks them in ir.vloads."""
+    ir.vloads = set()
+    if not st.lay["vglobal"]:
+        return ir
+    tab_of = {}
+    keyed = []
+    for idx, s in enumerate(ir.st):
+        key = float(idx)
+        if s[0] == "ldt":
+            tab_of[s[1]] = s[2]
+        elif s[0] == "lds":
+            _, v, ivar, imm, lc, care = s
+            lanes = range(care)
+            addrs = [imm + lc * 8 * l + (ir.tab[tab_of[ivar] + l] if ivar is not None else 0) for l in lanes]
+            inv = [st.in_v(a) for a in addrs]
+            assert all(inv) or not any(inv), "a load that mixes the value row's address space with shared memory"
+            if inv and inv[0]:
+                ir.vloads.add(v)
+                key = idx - dist
+                if ivar is not None and keyed and keyed[-1][2][0] == "ldt" and keyed[-1][2][1] == ivar:
+                    keyed[-1] = (key - 0.5, keyed[-1][1], keyed[-1][2])
+        keyed.append((key, idx, s))
+    keyed.sort(key=lambda t: (t[0], t[1]))
+    ir.st = [s for _, _, s in keyed]
     return ir
 
 
@@ -716,7 +796,7 @@ def print_function(ir: IR, out, fname, tabname, chunk=1500, bar=0):
         cuts.append(len(sts))
     defined_in = {}
     for idx, s in enumerate(sts):
-        if s[0] in ("ldt", "lds", "const", "add0", "msub", "msubp", "mul", "sub", "div", "regu", "shfl", "pne", "prange", "selc", "sel", "pnez", "add", "mulc", "chain"):
+        if s[0] in ("ldt", "lds", "const", "add0", "msub", "msubp", "mul", "sub", "div", "regu", "shfl", "pne", "prange", "pmask", "selc", "sel", "pnez", "add", "mulc", "chain"):
             defined_in[s[1]] = idx
 
     def uses(s):
@@ -749,15 +829,16 @@ def print_function(ir: IR, out, fname, tabname, chunk=1500, bar=0):
 
     # peephole: two loads of adjacent doubles (same addressing, 16-byte aligned, no store or sync between them)
     # become one ld.shared.v2.f64
+    vloads = getattr(ir, "vloads", set())
     paired, skip = {}, set()
     for idx, s in enumerate(sts):
-        if s[0] != "lds" or idx in skip or s[2] is not None or s[4] != 0 or s[3] % 16 != 0:
+        if s[0] != "lds" or idx in skip or s[2] is not None or s[4] != 0 or s[3] % 16 != 0 or s[1] in vloads:
             continue
         for j in range(idx + 1, min(idx + 12, len(sts))):
             t = sts[j]
             if t[0] in ("sts", "sync", "chain"):
                 break
-            if t[0] == "lds" and j not in skip and t[2] is None and t[4] == 0 and t[3] == s[3] + 8:
+            if t[0] == "lds" and j not in skip and t[2] is None and t[4] == 0 and t[3] == s[3] + 8 and t[1] not in vloads:
                 paired[idx] = t[1]
                 skip.add(j)
                 break
@@ -784,7 +865,7 @@ def print_function(ir: IR, out, fname, tabname, chunk=1500, bar=0):
         return {"d": "double", "i": "unsigned", "p": "bool"}[v[0]]
 
     for name, live_in, live_out, lo, hi in names:
-        args = ["const unsigned sb", "const unsigned sbl", "const unsigned lane", "const unsigned short *__restrict__ tl", "const unsigned nbar"]
+        args = ["const unsigned sb", "const unsigned sbl", "const unsigned lane", "const unsigned short *__restrict__ tl", "const unsigned nbar", "const char *vb", "const char *vbl"]
         args += [f"const {ctype(v)} {v}" for v in live_in]
         args += [f"{ctype(v)} &o_{v}" for v in live_out]
         out.append(f"static __device__ __noinline__ void {name}({', '.join(args)})\n{{")
@@ -805,6 +886,11 @@ def print_function(ir: IR, out, fname, tabname, chunk=1500, bar=0):
                 continue
             if k == "ldt":
                 out.append(f"\tconst unsigned {s[1]} = __ldg(tl + {s[2]});")
+            elif k == "lds" and s[1] in vloads:
+                # the value row: global memory (the warp's scratch row; vb is pre-offset so that slice offsets apply), L2 only
+                base = "vbl" if s[4] else "vb"
+                addr = f"{base} + {s[2]}" if s[2] else base
+                out.append(f"\tdouble {s[1]}; asm volatile(\"ld.global.cg.f64 %0, [%1+{s[3]}];\" : \"=d\"({s[1]}) : \"l\"({addr}));")
             elif k == "lds":
                 base = "sbl" if s[4] else "sb"
                 if s[2]:
@@ -852,20 +938,22 @@ def print_function(ir: IR, out, fname, tabname, chunk=1500, bar=0):
                 out.append(f"\tconst bool {s[1]} = {s[2]} != {s[3]}u;")
             elif k == "prange":
                 out.append(f"\tconst bool {s[1]} = lane - {s[2]}u <= {s[3] - s[2]}u;")
+            elif k == "pmask":
+                out.append(f"\tconst bool {s[1]} = ({s[2]:#x}u >> lane) & 1u;")
             else:
                 raise ValueError(k)
         for v in live_out:
             out.append(f"\to_{v} = {v};")
         out.append("}\n")
-    out.append(f"static __device__ __forceinline__ void {fname}(const unsigned sb, const unsigned nbar)\n{{")
-    out.append(f"\tconst unsigned lane = threadIdx.x & 31u, sbl = sb + 8u * lane;\n\tconst unsigned short *tl = {tabname} + lane;")
+    out.append(f"static __device__ __forceinline__ void {fname}(const unsigned sb, const unsigned nbar, const char *vb)\n{{")
+    out.append(f"\tconst unsigned lane = threadIdx.x & 31u, sbl = sb + 8u * lane;\n\tconst unsigned short *tl = {tabname} + lane;\n\tconst char *vbl = vb + 8u * lane;")
     declared = set()
     for name, live_in, live_out, lo, hi in names:
         for v in live_out:
             if v not in declared:
                 out.append(f"\t{ctype(v)} {v};")
                 declared.add(v)
-        out.append(f"\t{name}({', '.join(['sb', 'sbl', 'lane', 'tl', 'nbar'] + live_in + live_out)});")
+        out.append(f"\t{name}({', '.join(['sb', 'sbl', 'lane', 'tl', 'nbar', 'vb', 'vbl'] + live_in + live_out)});")
     out.append("}\n")
 
 

@@ -948,8 +948,9 @@ qp_int QPB_WBC_FORMULATE_DEVICE(QPBatch *B, int kind, qp_int count, const qp_rea
 	out.Ppr = dPpr; out.Apr = dApr; out.Gpr = dGpr; out.c = dc; out.h = dh; out.b = db;
 	out.nnzP = (int)pl.nnzP; out.nnzA = (int)pl.nnzA; out.nnzG = (int)pl.nnzG; out.n = (int)pl.n; out.m = (int)pl.m; out.p = (int)pl.p;
 	const int warps = 8;
-	const long grid = std::min<long>((count + warps - 1) / warps, (long)B->sm_count * 7);
-	wbc_formulate_kernel<<<(unsigned)grid, warps * 32, warps * WBC_SMEM * sizeof(double), (cudaStream_t)stream>>>(dstate, B->d_wbc_desc, B->d_wbc_consts, out, dindex, dcount_ptr, (int)count);
+	const long grid = std::min<long>((count + warps - 1) / warps, (long)B->sm_count * 2);
+	const size_t smem = warps * WBC_SMEM * sizeof(double) + B->wbc.desc.size() * sizeof(unsigned);
+	wbc_formulate_kernel<<<(unsigned)grid, warps * 32, smem, (cudaStream_t)stream>>>(dstate, B->d_wbc_desc, B->d_wbc_consts, out, dindex, dcount_ptr, (int)count);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }

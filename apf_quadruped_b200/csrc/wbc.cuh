@@ -198,7 +198,7 @@ struct WbcOut
 };
 
 // The rare formulas (the 6-term dot products of the cost, the limits): out of the copy path's way.
-__device__ __noinline__ double wbc_eval_formula(const unsigned op, const unsigned flag, const unsigned a, const unsigned b, const double *S)
+__device__ __forceinline__ double wbc_eval_formula(const unsigned op, const unsigned flag, const unsigned a, const unsigned b, const double *S)
 {
 	double v;
 	switch (op) {
@@ -229,39 +229,61 @@ __device__ __forceinline__ double wbc_eval(const unsigned d, const double *S)
 	return flag ? -v : v;
 }
 
+constexpr int WBC_ROUNDS = (WBC_STATE / 2 + 31) / 32; // 16-byte loads per lane and state row
+
+__device__ __forceinline__ void wbc_fetch(double2 (&nxt)[WBC_ROUNDS], const double *__restrict__ state, const int r, const int lane)
+{
+	const double2 *src = reinterpret_cast<const double2 *>(state + (size_t)r * WBC_STATE);
+#pragma unroll
+	for (int k = 0; k < WBC_ROUNDS; ++k)
+		if (lane + 32 * k < WBC_STATE / 2) nxt[k] = __ldcs(src + lane + 32 * k);
+}
+
+__device__ __forceinline__ void wbc_emit(double *__restrict__ row, const unsigned *sdesc, const int len, const double *S, const int lane)
+{
+	for (int e0 = lane; e0 < len; e0 += 128) { // four entries per lane in flight
+		double v[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			if (e0 + 32 * j < len) v[j] = wbc_eval(sdesc[e0 + 32 * j], S);
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			if (e0 + 32 * j < len) __stcs(row + e0 + 32 * j, v[j]);
+	}
+}
+
 // One warp per robot at a time, grid-stride over the robots (or over the list `index[0 .. *count_ptr)`).  Rows are
-// written at the robot's own index.
-__global__ void __launch_bounds__(256) wbc_formulate_kernel(const double *__restrict__ state, const unsigned *__restrict__ desc, const double *__restrict__ consts, const WbcOut out, const int *__restrict__ index, const int *__restrict__ count_ptr, const int count)
+// written at the robot's own index.  The formula table sits in shared memory (one copy per CTA), and the NEXT robot's
+// state row is already on its way (in registers) while the current one is turned into its value rows.
+__global__ void __launch_bounds__(256, 2) wbc_formulate_kernel(const double *__restrict__ state, const unsigned *__restrict__ desc, const double *__restrict__ consts, const WbcOut out, const int *__restrict__ index, const int *__restrict__ count_ptr, const int count)
 {
 	extern __shared__ __align__(16) double wsm[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+	const int nV = out.nnzP + out.nnzA + out.nnzG, total = nV + out.n + out.m + out.p;
+	unsigned *sdesc = reinterpret_cast<unsigned *>(wsm + warps * WBC_SMEM);
+	for (int i = threadIdx.x; i < total; i += blockDim.x) sdesc[i] = __ldg(desc + i);
 	double *S = wsm + warp * WBC_SMEM;
 	for (int i = lane; i < WBC_SMEM - WBC_STATE; i += 32) S[WBC_STATE + i] = consts[i];
+	__syncthreads();
 	const int limit = count_ptr ? min(*count_ptr, count) : count;
-	const int nV = out.nnzP + out.nnzA + out.nnzG;
-	for (int t = blockIdx.x * warps + warp; t < limit; t += gridDim.x * warps) {
+	const int stride = gridDim.x * warps;
+	double2 nxt[WBC_ROUNDS];
+	int t = blockIdx.x * warps + warp;
+	if (t < limit) wbc_fetch(nxt, state, index ? index[t] : t, lane);
+	for (; t < limit; t += stride) {
 		const int r = index ? index[t] : t;
 		__syncwarp();
-		const double2 *src = reinterpret_cast<const double2 *>(state + (size_t)r * WBC_STATE);
-		for (int i = lane; i < WBC_STATE / 2; i += 32) reinterpret_cast<double2 *>(S)[i] = __ldcs(src + i);
+#pragma unroll
+		for (int k = 0; k < WBC_ROUNDS; ++k)
+			if (lane + 32 * k < WBC_STATE / 2) reinterpret_cast<double2 *>(S)[lane + 32 * k] = nxt[k];
 		__syncwarp();
-		auto emit = [&](double *__restrict__ row, const int base, const int len) {
-			for (int e0 = lane; e0 < len; e0 += 128) { // four entries per lane in flight
-				double v[4];
-#pragma unroll
-				for (int j = 0; j < 4; ++j)
-					if (e0 + 32 * j < len) v[j] = wbc_eval(__ldg(desc + base + e0 + 32 * j), S);
-#pragma unroll
-				for (int j = 0; j < 4; ++j)
-					if (e0 + 32 * j < len) __stcs(row + e0 + 32 * j, v[j]);
-			}
-		};
-		emit(out.Ppr + (size_t)r * out.nnzP, 0, out.nnzP);
-		emit(out.Apr + (size_t)r * out.nnzA, out.nnzP, out.nnzA);
-		emit(out.Gpr + (size_t)r * out.nnzG, out.nnzP + out.nnzA, out.nnzG);
-		emit(out.c + (size_t)r * out.n, nV, out.n);
-		emit(out.h + (size_t)r * out.m, nV + out.n, out.m);
-		emit(out.b + (size_t)r * out.p, nV + out.n + out.m, out.p);
+		if (t + stride < limit) wbc_fetch(nxt, state, index ? index[t + stride] : t + stride, lane);
+		wbc_emit(out.Ppr + (size_t)r * out.nnzP, sdesc, out.nnzP, S, lane);
+		wbc_emit(out.Apr + (size_t)r * out.nnzA, sdesc + out.nnzP, out.nnzA, S, lane);
+		wbc_emit(out.Gpr + (size_t)r * out.nnzG, sdesc + out.nnzP + out.nnzA, out.nnzG, S, lane);
+		wbc_emit(out.c + (size_t)r * out.n, sdesc + nV, out.n, S, lane);
+		wbc_emit(out.h + (size_t)r * out.m, sdesc + nV + out.n, out.m, S, lane);
+		wbc_emit(out.b + (size_t)r * out.p, sdesc + nV + out.n + out.m, out.p, S, lane);
 	}
 }
 
