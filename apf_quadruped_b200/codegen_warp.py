@@ -683,7 +683,7 @@ def gen_solve(st: Structure, passes=None) -> IR:
         v = ir.gather([X(j) for j in js], X(js[0]), tail_any=True)
         ir.scatter([(lay["rhs"] + st.P[j]) * 8 for j in js], v)
     ir.emit("sync")
-    return ir
+    return hoist_v_loads(ir, st)  # (no value-row loads here: the tables of per-lane offsets are requested early)
 
 
 def gen_resid(st: Structure) -> IR:
@@ -749,19 +749,24 @@ def gen_resid(st: Structure) -> IR:
     return hoist_v_loads(ir, st)
 
 
-def hoist_v_loads(ir: IR, st: Structure, dist=120):
+def hoist_v_loads(ir: IR, st: Structure, dist=None, tdist=None):
     """Value-row loads (global memory, an L2 round trip each) are moved `dist` statements ahead of where the program
     needs them -- together with the table load that feeds them -- so that they are in flight while the warp works on
     shared memory.  Legal anywhere: the value row is read-only while the programs run.  Marks them in ir.vloads."""
     ir.vloads = set()
     if not st.lay["vglobal"]:
         return ir
+    dist = int(os.environ.get("QPB_GEN_VDIST", "100")) if dist is None else dist
+    # the tables of per-lane offsets are global loads too, and with the slices filling shared memory the L1 that would
+    # hold them is a few KB: they come from L2, so they are requested early as well
+    tdist = int(os.environ.get("QPB_GEN_TDIST", "60")) if tdist is None else tdist
     tab_of = {}
     keyed = []
     for idx, s in enumerate(ir.st):
         key = float(idx)
         if s[0] == "ldt":
             tab_of[s[1]] = s[2]
+            key = idx - tdist
         elif s[0] == "lds":
             _, v, ivar, imm, lc, care = s
             lanes = range(care)
@@ -957,11 +962,11 @@ def print_function(ir: IR, out, fname, tabname, chunk=1500, bar=0):
     out.append("}\n")
 
 
-def generate(kind: str, chunk=1500, bar=0):
+def generate(kind: str, chunk=1500, bar=0, vglobal=True):
     from . import dogbot, qpswift as Q
     plan = Q.Plan(dogbot.generate(kind, 1).pattern)
     key = plan.stream_key()
-    st = Structure(plan)
+    st = Structure(plan, vglobal)
     progs = (gen_factor(st), gen_solve(st), gen_resid(st))
     out = [f"// GENERATED by apf_quadruped_b200/codegen_warp.py for the '{kind}' pattern (pattern key {key:#018x}); do not edit.",
            f"// passes: {[(r[0], r[-1]) for r in progs[0].passes]}",
@@ -971,19 +976,29 @@ def generate(kind: str, chunk=1500, bar=0):
         vals = ", ".join(str(v) for v in ir.tab) or "0"
         out.append(f"__device__ const unsigned short {tabname}[] = {{{vals}}};\n")
         print_function(ir, out, ir.name, tabname, chunk, bar if ir.name != "resid" else 0)
+    lay = st.lay
+    # what the kernel gets: the shared-memory part of the slice (V outside it: in the warp's global scratch row)
+    clay = dict(lay)
+    if lay["vglobal"]:
+        clay["V"] = lay["smem"]
+    clay["total"] = lay["smem"]
+    nv = len(st.pattern.Pir) + len(st.pattern.Air) + len(st.pattern.Gir)
+    max_warps = max(1, min(int(os.environ.get("QPB_GEN_MAX_WARPS", "10")), (227 * 1024) // (lay["smem"] * 8)))
     out += ["struct Prog", "{",
             "\tstatic constexpr bool own_residuals = true;",
             "\tstatic constexpr bool realign = %s; // barriers inside factor / solve need every warp's count" % ("true" if bar else "false"),
-            "\tstatic __device__ __forceinline__ void factor(const ProgramView &, const unsigned sb, const unsigned nbar) { genw_%s::factor(sb, nbar); }" % kind,
-            "\tstatic __device__ __forceinline__ void solve(const ProgramView &, const unsigned sb, const unsigned nbar) { genw_%s::solve(sb, nbar); }" % kind,
-            "\tstatic __device__ __forceinline__ void resid(const unsigned sb) { genw_%s::resid(sb, 32u); }" % kind,
+            "\tstatic constexpr bool value_row_global = %s; // V = P | A | G in the warp's scratch row in global memory, not in the slice" % ("true" if lay["vglobal"] else "false"),
+            "\tstatic constexpr int value_row_doubles = %d; // nV + the zero behind it, padded" % (lay["total"] - lay["smem"] if lay["vglobal"] else 0),
+            "\tstatic __device__ __forceinline__ void factor(const ProgramView &, const unsigned sb, const unsigned nbar, const char *vb) { genw_%s::factor(sb, nbar, vb); }" % kind,
+            "\tstatic __device__ __forceinline__ void solve(const ProgramView &, const unsigned sb, const unsigned nbar, const char *vb) { genw_%s::solve(sb, nbar, vb); }" % kind,
+            "\tstatic __device__ __forceinline__ void resid(const unsigned sb, const char *vb) { genw_%s::resid(sb, 32u, vb); }" % kind,
             "};", "", f"}} // namespace genw_{kind}", "",
-            "static const SliceLayout layout_%s = {%s};" % (kind, ", ".join(str(st.lay[f]) for f in LAYOUT_FIELDS)),
-            f"QPB_REGISTER_GENERATED_WARP({kind}, {key:#018x}ull, layout_{kind}, genw_{kind}::Prog)", "", "} // namespace qpb", ""]
+            "static const SliceLayout layout_%s = {%s};" % (kind, ", ".join(str(clay[f]) for f in LAYOUT_FIELDS)),
+            f"QPB_REGISTER_GENERATED_WARP({kind}, {key:#018x}ull, layout_{kind}, genw_{kind}::Prog, {max_warps})", "", "} // namespace qpb", ""]
     stats = {ir.name: dict(statements=len(ir.st), table=len(ir.tab),
                            **{k: sum(1 for s in ir.st if s[0] == k) for k in ("lds", "sts", "ldt", "msub", "div", "sync", "shfl", "chain")})
              for ir in progs}
-    stats["layout"] = dict(total=st.lay["total"], bytes=st.lay["total"] * 8, tsize=st.lay["tsize"])
+    stats["layout"] = dict(smem=st.lay["smem"], bytes=st.lay["smem"] * 8, tsize=st.lay["tsize"], value_row_global=lay["vglobal"], nV=nv, max_warps=max_warps)
     plan.close()
     return "\n".join(out), stats
 
@@ -994,10 +1009,11 @@ def main():
     ap.add_argument("--out", default="build/gen")
     ap.add_argument("--chunk", type=int, default=1500)
     ap.add_argument("--bar", type=int, default=0, help="a CTA barrier about every so many statements of factor / solve (0: none)")
+    ap.add_argument("--vsmem", action="store_true", help="keep the value row P | A | G in shared memory (fewer warps per SM) instead of in the warp's global scratch row")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     for kind in a.kinds:
-        src, stats = generate(kind, a.chunk, a.bar)
+        src, stats = generate(kind, a.chunk, a.bar, not a.vsmem)
         path = os.path.join(a.out, f"warp_gen_{kind}.cu")
         old = open(path).read() if os.path.exists(path) else None
         if old != src:

@@ -62,9 +62,9 @@ static std::vector<GeneratedWarpKernel> &generated_warp_kernels()
 	static std::vector<GeneratedWarpKernel> v;
 	return v;
 }
-void register_generated_warp_kernel(unsigned long long key, const void *kernel, const void *kernel_free, const char *name, const SliceLayout &lay)
+void register_generated_warp_kernel(unsigned long long key, const void *kernel, const void *kernel_free, const char *name, const SliceLayout &lay, int max_warps, int value_row_doubles)
 {
-	generated_warp_kernels().push_back(GeneratedWarpKernel{key, kernel, kernel_free, name, lay});
+	generated_warp_kernels().push_back(GeneratedWarpKernel{key, kernel, kernel_free, name, lay, max_warps, value_row_doubles});
 }
 const GeneratedWarpKernel *find_generated_warp_kernel(unsigned long long key)
 {
@@ -158,6 +158,7 @@ struct QPBatch
 	int *d_counter = nullptr;
 	int *d_spill = nullptr; // [capacity] QPs the throughput kernel handed over, d_counter[48] = how many
 	double *d_spill_sigma = nullptr; // [capacity] sigma of a handed-over QP
+	double *d_vscratch = nullptr;    // value rows of the QPs in flight (generated warp-per-QP kernels that keep V outside the slice)
 	ProgramView pview;
 	int max_warps = 1;      // slices of shared memory that fit next to each other in one CTA
 	// throughput kernel (stream.cuh)
@@ -227,10 +228,12 @@ static int batch_alloc(QPBatch *B)
 		const GeneratedWarpKernel *g = find_generated_warp_kernel(stream_program_key(B->sprog));
 		if (g) {
 			B->gen_warp = g;
-			B->gen_warps = (int)std::min<size_t>(GEN_WARPS_PER_CTA, B->smem_limit / ((size_t)g->lay.total * sizeof(double)));
+			B->gen_warps = (int)std::min<size_t>((size_t)g->max_warps, B->smem_limit / ((size_t)g->lay.total * sizeof(double)));
 			if (getenv("QPB_WARP_WARPS")) B->gen_warps = std::max(1, std::min(B->gen_warps, atoi(getenv("QPB_WARP_WARPS"))));
 			CUDA_TRY(cudaFuncSetAttribute(g->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
 			CUDA_TRY(cudaFuncSetAttribute(g->kernel_free, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
+			if (g->value_row_doubles) // one scratch row per warp of the largest grid (+ a tail: lanes beyond a row's end may read past it)
+				CUDA_TRY(cudaMalloc(&B->d_vscratch, ((size_t)B->sm_count * g->max_warps * g->value_row_doubles + 64) * sizeof(double)));
 		}
 	}
 	CUDA_TRY(cudaFuncSetAttribute(ldl_numeric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
@@ -325,7 +328,9 @@ static int launch_latency(QPBatch *B, const BatchIO &io, const SolveParams &prm,
 	const size_t smem = (size_t)warps * lay.total * sizeof(double);
 	if (B->gen_warp) {
 		const int *plan = B->d_plan;
-		void *args[] = {&plan, &B->pview, const_cast<SliceLayout *>(&lay), const_cast<BatchIO *>(&io), const_cast<SolveParams *>(&prm), &counter};
+		BatchIO gio = io;
+		gio.vscratch = B->d_vscratch;
+		void *args[] = {&plan, &B->pview, const_cast<SliceLayout *>(&lay), &gio, const_cast<SolveParams *>(&prm), &counter};
 		CUDA_TRY(cudaLaunchKernel(getenv("QPB_WARP_FREE") && !io.server_done ? B->gen_warp->kernel_free : B->gen_warp->kernel, dim3((unsigned)grid), dim3((unsigned)warps * 32), args, smem, st));
 	} else qp_solve_warp_kernel<InterpretedWaves, MAX_WARPS_PER_CTA, true><<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->d_plan, B->pview, B->program.lay, io, prm, counter);
 	CUDA_TRY(cudaGetLastError());
@@ -565,6 +570,7 @@ void QP_CLEANUP_BATCH(QPBatch *B)
 	cudaFree(B->d_prog);
 	cudaFree(B->d_stream);
 	cudaFree(B->d_spill_sigma);
+	cudaFree(B->d_vscratch);
 	for (int k = 0; k < 3; ++k) { cudaFree(B->d_dense_map[k]); cudaFree(B->d_dense[k]); }
 	cudaFree(B->d_violation);
 	cudaFree(B->d_single);

@@ -63,6 +63,9 @@ struct BatchIO
 	// LDL_numeric (stats->ldl_numeric, Auxilary.c:476-484); row 1 + it: fval, n_rx, n_ry, n_rz, n_mu at the top of
 	// iteration it (qpSWIFT.c:513-516) and the step lengths it ends with (598-601).  Null: no trace.
 	double *trace;
+	// warp-per-QP kernels whose programs keep the value row P | A | G outside the slice: one scratch row per warp of the
+	// grid (GeneratedWarpKernel::value_row_doubles each) in global memory
+	double *vscratch;
 };
 
 #ifdef __CUDACC__

@@ -29,18 +29,20 @@ struct ProgramView
 
 enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_PRED = 2, MODE_CENT = 3 };
 static const int MAX_WARPS_PER_CTA = 16; // interpreted schedules: 128 registers per thread
-static const int GEN_WARPS_PER_CTA = 8;  // generated programs keep a row's work vector in registers: 255 per thread
+static const int GEN_WARPS_MAX = 16;     // generated programs: as many warps per CTA as their slices fit (trot 12, crawl 10, stance 9)
 
 struct GeneratedWarpKernel
 {
 	unsigned long long key; // stream_program_key of the pattern the code was generated for
-	const void *kernel;     // qp_solve_warp_kernel<PROG, GEN_WARPS_PER_CTA, true>
-	const void *kernel_free; // ... <PROG, GEN_WARPS_PER_CTA, false>: the warps of a CTA never wait for one another
+	const void *kernel;     // qp_solve_warp_kernel<PROG, max_warps, true>
+	const void *kernel_free; // ... <PROG, max_warps, false>: the warps of a CTA never wait for one another
 	const char *name;
 	SliceLayout lay;        // the layout the addresses in the code assume (scratch cut down to what the code uses)
+	int max_warps;          // warps per CTA the kernel was compiled for (its register budget follows: 65,536 / (32 max_warps))
+	int value_row_doubles;  // > 0: the value row P | A | G lives in a scratch row of that many doubles per warp in GLOBAL memory
 };
 
-void register_generated_warp_kernel(unsigned long long key, const void *kernel, const void *kernel_free, const char *name, const SliceLayout &lay);
+void register_generated_warp_kernel(unsigned long long key, const void *kernel, const void *kernel_free, const char *name, const SliceLayout &lay, int max_warps, int value_row_doubles);
 const GeneratedWarpKernel *find_generated_warp_kernel(unsigned long long key);
 
 #ifdef __CUDACC__
@@ -75,9 +77,11 @@ struct InterpretedWaves
 {
 	static constexpr bool own_residuals = false;
 	static constexpr bool realign = true;
-	static __device__ __forceinline__ void resid(const unsigned) {}
-	static __device__ __forceinline__ void factor(const ProgramView &pg, const unsigned sb, unsigned) { run_segment(pg.words, pg.f_first, pg.f_waves, pg.f_width, sb); }
-	static __device__ __forceinline__ void solve(const ProgramView &pg, const unsigned sb, unsigned) { run_segment(pg.words, pg.s_first, pg.s_waves, pg.s_width, sb); }
+	static constexpr bool value_row_global = false;
+	static constexpr int value_row_doubles = 0;
+	static __device__ __forceinline__ void resid(const unsigned, const char *) {}
+	static __device__ __forceinline__ void factor(const ProgramView &pg, const unsigned sb, unsigned, const char *) { run_segment(pg.words, pg.f_first, pg.f_waves, pg.f_width, sb); }
+	static __device__ __forceinline__ void solve(const ProgramView &pg, const unsigned sb, unsigned, const char *) { run_segment(pg.words, pg.s_first, pg.s_waves, pg.s_width, sb); }
 };
 
 template <class PROG, int MAXW, bool CTA_SYNC>
@@ -90,6 +94,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 	const unsigned sb = (unsigned)__cvta_generic_to_shared(S);
 	WarpState w = carve(S, lay);
 	if (lane == 0) { S[lay.zero] = 0.0; S[lay.zero + 1] = -0.0; }
+	// Generated programs for the DogBot patterns keep the value row V = P | A | G -- read-only during a solve, a third
+	// of the working set -- in the warp's own scratch row in GLOBAL memory (L2-resident: a few MB for the whole grid)
+	// instead of in the slice: 18.7 KB of shared memory per QP instead of 26.2 KB (trot), i.e. 12 warps per SM instead
+	// of 8.  The programs address slice and scratch row as ONE space: a byte offset >= lay.V * 8 is in the scratch row.
+	const char *vb = nullptr;
+	if (PROG::value_row_global) {
+		double *vrow = io.vscratch + ((size_t)blockIdx.x * MAXW + warp) * PROG::value_row_doubles;
+		w.V = vrow;
+		vb = reinterpret_cast<const char *>(vrow) - (size_t)lay.V * sizeof(double);
+		if (lane == 0) { vrow[PROG::value_row_doubles - 2] = 0.0; vrow[PROG::value_row_doubles - 1] = 0.0; } // the zero behind the row
+	}
 	__syncwarp();
 	const int n = pv.n, m = pv.m, p = pv.p;
 	const double thr = prm.reltol / sqrt(3.0);
@@ -109,7 +124,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 			double mu_next = mu; // (mu is updated after the stop test, qpSWIFT.c:538: a QP that leaves keeps the last one)
 			if (iters >= prm.maxit) flag = 2; // QP_MAXIT (qpSWIFT.c:604-607)
 			else {
-				if (PROG::own_residuals) PROG::resid(sb);
+				if (PROG::own_residuals) PROG::resid(sb, vb);
 				else ipm_residual_products(pv, w.V, w.c, w.h, w.b, w.x, w.y, w.z, w.s, w.r, S + lay.T /* scratch: -(P x) */);
 				const IterSums sums = ipm_sums(n, m, p, sb, lay, lay.T);
 				sc = sums.sc;
@@ -198,6 +213,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 					warp_copy_in(w.h, io.h + qi * m, m);
 					if (p) warp_copy_in(w.b, io.b + qi * p, p);
 				}
+				if (PROG::value_row_global) __threadfence_block(); // (the row was written through w.V by other lanes: visible before it is read)
 				__syncwarp();
 				if (resume_at > 0 && io.spill_sigma) {
 					// the state of QP_SOLVE's loop between two iterations is (x, y, z, s, sigma, IterationCount);
@@ -233,9 +249,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 		if (mode != MODE_IDLE) {
 			long long t0 = 0;
 			if (io.trace) t0 = (long long)globaltimer_ns();
-			PROG::factor(pg, sb, busy);
+			PROG::factor(pg, sb, busy, vb);
 			if (io.trace) ldl_ns += (long long)globaltimer_ns() - t0;
-			PROG::solve(pg, sb, busy);
+			PROG::solve(pg, sb, busy, vb);
 		}
 		if (mode == MODE_INIT) {
 			ipm_init_point(pv, w);
@@ -246,7 +262,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 		}
 		// (re-aligns the warps where the program wants that: interpreted schedules stream their words together)
 		const unsigned again = CTA_SYNC && PROG::realign ? (unsigned)__syncthreads_count(mode == MODE_PRED) : 32u;
-		if (mode == MODE_PRED) PROG::solve(pg, sb, again);
+		if (mode == MODE_PRED) PROG::solve(pg, sb, again, vb);
 		if (mode == MODE_PRED || mode == MODE_CENT) { // step, damping, update (qpSWIFT.c:584-596)
 			ipm_recover_and_steplength(n, m, p, w, ap, ad);
 			ipm_update(n, m, p, w, ap, ad);
@@ -259,16 +275,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 	}
 }
 
-#define QPB_REGISTER_GENERATED_WARP(tag, key, layout, PROG)                                                                          \
-	template __global__ void qp_solve_warp_kernel<PROG, GEN_WARPS_PER_CTA, true>(const int *__restrict__, ProgramView, SliceLayout, BatchIO, SolveParams, int *__restrict__);  \
-	template __global__ void qp_solve_warp_kernel<PROG, GEN_WARPS_PER_CTA, false>(const int *__restrict__, ProgramView, SliceLayout, BatchIO, SolveParams, int *__restrict__); \
+#define QPB_REGISTER_GENERATED_WARP(tag, key, layout, PROG, MAXW)                                                                    \
+	template __global__ void qp_solve_warp_kernel<PROG, MAXW, true>(const int *__restrict__, ProgramView, SliceLayout, BatchIO, SolveParams, int *__restrict__);  \
+	template __global__ void qp_solve_warp_kernel<PROG, MAXW, false>(const int *__restrict__, ProgramView, SliceLayout, BatchIO, SolveParams, int *__restrict__); \
 	namespace {                                                                                                                           \
 	struct RegisterWarp_##tag                                                                                                             \
 	{                                                                                                                                     \
 		RegisterWarp_##tag()                                                                                                              \
 		{                                                                                                                                 \
-			register_generated_warp_kernel(key, reinterpret_cast<const void *>(&qp_solve_warp_kernel<PROG, GEN_WARPS_PER_CTA, true>),     \
-			                               reinterpret_cast<const void *>(&qp_solve_warp_kernel<PROG, GEN_WARPS_PER_CTA, false>), #tag, layout); \
+			register_generated_warp_kernel(key, reinterpret_cast<const void *>(&qp_solve_warp_kernel<PROG, MAXW, true>),                  \
+			                               reinterpret_cast<const void *>(&qp_solve_warp_kernel<PROG, MAXW, false>), #tag, layout, MAXW,  \
+			                               PROG::value_row_global ? PROG::value_row_doubles : 0);                                         \
 		}                                                                                                                                 \
 	} register_warp_##tag;                                                                                                                \
 	}

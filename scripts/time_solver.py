@@ -25,6 +25,10 @@ VARIANTS = {
     "warp2": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_WARPS": "2"},
     "warp3": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_WARPS": "3"},
     "warp7": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_WARPS": "7"},
+    "warp8": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_WARPS": "8"},
+    "warp9": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_WARPS": "9"},
+    "warp10": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_WARPS": "10"},
+    "warp11": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_WARPS": "11"},
 }
 
 

@@ -16,6 +16,7 @@ def make_slice(lay, batch, i):
     S = np.full(lay["total"], np.nan)
     S[lay["zero"]] = 0.0
     S[lay["zero"] + 1] = -0.0
+    S[lay["vzero"]] = 0.0  # (the zero behind the value row, in the value row's address space)
     vals = np.concatenate([batch.Ppr[i], batch.Apr[i], batch.Gpr[i]])
     S[lay["V"]:lay["V"] + vals.size] = vals + 0.0  # (the kernel normalises -0.0 to +0.0 when it loads the values)
     S[lay["c"]:lay["c"] + pat.n] = batch.c[i]
@@ -125,5 +126,6 @@ def test_layout_fits_more_warps_than_the_interpreted_one(qps):
         plan = qps.Plan(dogbot.generate(kind, 1).pattern)
         st = W.Structure(plan)
         full = plan.layout()
-        assert st.lay["total"] < full["total"] and st.lay["tsize"] >= 2 * plan.pattern.m
+        assert st.lay["smem"] < st.lay["total"] < full["total"] and st.lay["tsize"] >= 2 * plan.pattern.m
+        assert st.lay["V"] >= st.lay["smem"], "the value row lies outside the shared-memory part of the slice"
         assert all(st.lay[k] % 2 == 0 for k in W.LAYOUT_FIELDS if k not in ("total", "tsize"))
