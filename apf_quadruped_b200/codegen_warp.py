@@ -989,6 +989,9 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
             "\tstatic constexpr bool realign = %s; // barriers inside factor / solve need every warp's count" % ("true" if bar else "false"),
             "\tstatic constexpr bool value_row_global = %s; // V = P | A | G in the warp's scratch row in global memory, not in the slice" % ("true" if lay["vglobal"] else "false"),
             "\tstatic constexpr int value_row_doubles = %d; // nV + the zero behind it, padded" % (lay["total"] - lay["smem"] if lay["vglobal"] else 0),
+            "\tstatic constexpr bool static_shape = true;",
+            "\tstatic constexpr int kN = %d, kM = %d, kP = %d, kOffA = %d, kOffG = %d, kNV = %d;" % (st.n, st.m, st.p, len(st.pattern.Pir), len(st.pattern.Pir) + len(st.pattern.Air), nv),
+            "\tstatic __device__ __forceinline__ SliceLayout layout() { SliceLayout L; %s return L; }" % " ".join(f"L.{f} = {clay[f]};" for f in LAYOUT_FIELDS),
             "\tstatic __device__ __forceinline__ void factor(const ProgramView &, const unsigned sb, const unsigned nbar, const char *vb) { genw_%s::factor(sb, nbar, vb); }" % kind,
             "\tstatic __device__ __forceinline__ void solve(const ProgramView &, const unsigned sb, const unsigned nbar, const char *vb) { genw_%s::solve(sb, nbar, vb); }" % kind,
             "\tstatic __device__ __forceinline__ void resid(const unsigned sb, const char *vb) { genw_%s::resid(sb, 32u, vb); }" % kind,

@@ -79,16 +79,23 @@ struct InterpretedWaves
 	static constexpr bool realign = true;
 	static constexpr bool value_row_global = false;
 	static constexpr int value_row_doubles = 0;
+	static constexpr bool static_shape = false; // sizes and layout come with the launch
+	static constexpr int kN = 0, kM = 0, kP = 0, kOffA = 0, kOffG = 0, kNV = 0;
+	static __device__ __forceinline__ SliceLayout layout() { return SliceLayout(); }
 	static __device__ __forceinline__ void resid(const unsigned, const char *) {}
 	static __device__ __forceinline__ void factor(const ProgramView &pg, const unsigned sb, unsigned, const char *) { run_segment(pg.words, pg.f_first, pg.f_waves, pg.f_width, sb); }
 	static __device__ __forceinline__ void solve(const ProgramView &pg, const unsigned sb, unsigned, const char *) { run_segment(pg.words, pg.s_first, pg.s_waves, pg.s_width, sb); }
 };
 
 template <class PROG, int MAXW, bool CTA_SYNC>
-__global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *__restrict__ plan, ProgramView pg, SliceLayout lay, BatchIO io, SolveParams prm, int *__restrict__ counter)
+__global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *__restrict__ plan, ProgramView pg, SliceLayout lay_arg, BatchIO io, SolveParams prm, int *__restrict__ counter)
 {
 	extern __shared__ __align__(16) double smem[];
-	const PlanView pv = view_of(plan);
+	// A generated program knows its pattern's sizes and slice layout at compile time: the elementwise steps below then
+	// unroll, and every address in them is the slice base plus a constant.
+	const SliceLayout lay = PROG::static_shape ? PROG::layout() : lay_arg;
+	PlanView pv = view_of(plan);
+	if (PROG::static_shape) { pv.n = PROG::kN; pv.m = PROG::kM; pv.p = PROG::kP; pv.N = PROG::kN + PROG::kM + PROG::kP; pv.offA = PROG::kOffA; pv.offG = PROG::kOffG; pv.nV = PROG::kNV; }
 	const int lane = lane_id(), warp = threadIdx.x >> 5;
 	double *S = smem + (size_t)warp * lay.total;
 	const unsigned sb = (unsigned)__cvta_generic_to_shared(S);
