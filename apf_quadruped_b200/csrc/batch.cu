@@ -270,10 +270,10 @@ static int batch_alloc(QPBatch *B)
 		B->stream_slots = std::min(full, (B->capacity + 31) / 32);
 		// Which kernel takes a batch.  Without a pattern-specialised warp-per-QP kernel: the throughput kernel from
 		// 2048 QPs on.  With one (DogBot trot / stance / crawl): the warp-per-QP kernel keeps the factor in shared
-		// memory, has no tail (1,184 QPs in flight instead of 37,888) and no stragglers' hand-over, and matches the
-		// throughput kernel up to a few waves of its lanes; beyond three waves (113,664 QPs) the throughput kernel's
-		// tail no longer matters and it is the faster one.  QPB_STREAM_MIN overrides.
-		B->stream_min = getenv("QPB_STREAM_MIN") ? atol(getenv("QPB_STREAM_MIN")) : (B->gen_warp ? 3 * full * 32 : 2048);
+		// memory, has no tail (1,480 QPs in flight instead of 37,888) and no stragglers' hand-over, and since round 2
+		// (value row outside the slice: 10 warps per SM) it is the faster one at every batch size measured
+		// (trot 65,536: 1.70 M against 1.40 M solves/s; 262,144: 1.71 M against 1.63 M).  QPB_STREAM_MIN overrides.
+		B->stream_min = getenv("QPB_STREAM_MIN") ? atol(getenv("QPB_STREAM_MIN")) : (B->gen_warp ? LONG_MAX : 2048);
 		// A pattern whose window leaves room for fewer than 4 warps per SM (e.g. the horizon-10 MPC QP:
 		// N = 600, one warp) is faster on the latency kernel; QPB_STREAM_MIN_WARPS overrides.
 		const long min_warps = getenv("QPB_STREAM_MIN_WARPS") ? atol(getenv("QPB_STREAM_MIN_WARPS")) : 4;
@@ -933,6 +933,7 @@ static int ensure_wbc(QPBatch *B, int kind)
 	if (B->d_wbc_desc && B->wbc.kind == kind) return 0;
 	if (B->d_wbc_desc) return fail(QPB_E_ARG, "WBC: this batch's pattern was bound to another contact pattern kind", cudaSuccess);
 	if (kind < 0 || kind > 2 || !wbc_build_tables(B->wbc, kind, B->plan)) { B->wbc.kind = -1; return fail(QPB_E_PATTERN, "WBC: the batch's sparsity pattern is not the DogBot pattern of that kind (0 stance, 1 trot, 2 crawl)", cudaSuccess); }
+	CUDA_TRY(cudaFuncSetAttribute(wbc_formulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 8 * WBC_SMEM * sizeof(double) + 8192)));
 	std::vector<uint32_t> packed(B->wbc.desc.size());
 	for (size_t i = 0; i < packed.size(); ++i) packed[i] = wbc_pack(B->wbc.desc[i]);
 	CUDA_TRY(cudaMalloc(&B->d_wbc_desc, packed.size() * sizeof(uint32_t)));
@@ -954,8 +955,8 @@ qp_int QPB_WBC_FORMULATE_DEVICE(QPBatch *B, int kind, qp_int count, const qp_rea
 	out.Ppr = dPpr; out.Apr = dApr; out.Gpr = dGpr; out.c = dc; out.h = dh; out.b = db;
 	out.nnzP = (int)pl.nnzP; out.nnzA = (int)pl.nnzA; out.nnzG = (int)pl.nnzG; out.n = (int)pl.n; out.m = (int)pl.m; out.p = (int)pl.p;
 	const int warps = 8;
-	const long grid = std::min<long>((count + warps - 1) / warps, (long)B->sm_count * 2);
-	const size_t smem = warps * WBC_SMEM * sizeof(double) + B->wbc.desc.size() * sizeof(unsigned);
+	const long grid = std::min<long>((count + warps - 1) / warps, (long)B->sm_count * 3);
+	const size_t smem = 2 * warps * WBC_SMEM * sizeof(double) + B->wbc.desc.size() * sizeof(unsigned);
 	wbc_formulate_kernel<<<(unsigned)grid, warps * 32, smem, (cudaStream_t)stream>>>(dstate, B->d_wbc_desc, B->d_wbc_consts, out, dindex, dcount_ptr, (int)count);
 	CUDA_TRY(cudaGetLastError());
 	return 0;

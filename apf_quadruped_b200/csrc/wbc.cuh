@@ -229,14 +229,15 @@ __device__ __forceinline__ double wbc_eval(const unsigned d, const double *S)
 	return flag ? -v : v;
 }
 
-constexpr int WBC_ROUNDS = (WBC_STATE / 2 + 31) / 32; // 16-byte loads per lane and state row
-
-__device__ __forceinline__ void wbc_fetch(double2 (&nxt)[WBC_ROUNDS], const double *__restrict__ state, const int r, const int lane)
+// The state row of robot r on its way into a warp's buffer: 16 bytes per lane and request, asynchronously
+// (cp.async: global -> shared memory without a stop in registers).
+__device__ __forceinline__ void wbc_fetch(double *buf, const double *__restrict__ state, const int r, const int lane)
 {
-	const double2 *src = reinterpret_cast<const double2 *>(state + (size_t)r * WBC_STATE);
-#pragma unroll
-	for (int k = 0; k < WBC_ROUNDS; ++k)
-		if (lane + 32 * k < WBC_STATE / 2) nxt[k] = __ldcs(src + lane + 32 * k);
+	const double *src = state + (size_t)r * WBC_STATE;
+	const unsigned dst = (unsigned)__cvta_generic_to_shared(buf);
+	for (int i = lane; i < WBC_STATE / 2; i += 32)
+		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (unsigned)i), "l"(src + 2 * i) : "memory");
+	asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 __device__ __forceinline__ void wbc_emit(double *__restrict__ row, const unsigned *sdesc, const int len, const double *S, const int lane)
@@ -253,37 +254,38 @@ __device__ __forceinline__ void wbc_emit(double *__restrict__ row, const unsigne
 }
 
 // One warp per robot at a time, grid-stride over the robots (or over the list `index[0 .. *count_ptr)`).  Rows are
-// written at the robot's own index.  The formula table sits in shared memory (one copy per CTA), and the NEXT robot's
-// state row is already on its way (in registers) while the current one is turned into its value rows.
-__global__ void __launch_bounds__(256, 2) wbc_formulate_kernel(const double *__restrict__ state, const unsigned *__restrict__ desc, const double *__restrict__ consts, const WbcOut out, const int *__restrict__ index, const int *__restrict__ count_ptr, const int count)
+// written at the robot's own index.  The formula table sits in shared memory (one copy per CTA); every warp has TWO
+// state buffers: while it turns one robot's state into its value rows, the next robot's state row is already arriving
+// in the other (cp.async), so the HBM round trip of the load is off the critical path.
+__global__ void __launch_bounds__(256, 3) wbc_formulate_kernel(const double *__restrict__ state, const unsigned *__restrict__ desc, const double *__restrict__ consts, const WbcOut out, const int *__restrict__ index, const int *__restrict__ count_ptr, const int count)
 {
 	extern __shared__ __align__(16) double wsm[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
 	const int nV = out.nnzP + out.nnzA + out.nnzG, total = nV + out.n + out.m + out.p;
-	unsigned *sdesc = reinterpret_cast<unsigned *>(wsm + warps * WBC_SMEM);
+	unsigned *sdesc = reinterpret_cast<unsigned *>(wsm + 2 * warps * WBC_SMEM);
 	for (int i = threadIdx.x; i < total; i += blockDim.x) sdesc[i] = __ldg(desc + i);
-	double *S = wsm + warp * WBC_SMEM;
-	for (int i = lane; i < WBC_SMEM - WBC_STATE; i += 32) S[WBC_STATE + i] = consts[i];
+	double *buf[2] = {wsm + (2 * warp) * WBC_SMEM, wsm + (2 * warp + 1) * WBC_SMEM};
+	for (int i = lane; i < WBC_SMEM - WBC_STATE; i += 32) { buf[0][WBC_STATE + i] = consts[i]; buf[1][WBC_STATE + i] = consts[i]; }
 	__syncthreads();
 	const int limit = count_ptr ? min(*count_ptr, count) : count;
 	const int stride = gridDim.x * warps;
-	double2 nxt[WBC_ROUNDS];
-	int t = blockIdx.x * warps + warp;
-	if (t < limit) wbc_fetch(nxt, state, index ? index[t] : t, lane);
-	for (; t < limit; t += stride) {
+	int t = blockIdx.x * warps + warp, cur = 0;
+	if (t < limit) wbc_fetch(buf[0], state, index ? index[t] : t, lane);
+	for (; t < limit; t += stride, cur ^= 1) {
 		const int r = index ? index[t] : t;
+		if (t + stride < limit) {
+			wbc_fetch(buf[cur ^ 1], state, index ? index[t + stride] : t + stride, lane);
+			asm volatile("cp.async.wait_group 1;" ::: "memory"); // the current robot's row has landed; the next one may still be in flight
+		} else asm volatile("cp.async.wait_group 0;" ::: "memory");
 		__syncwarp();
-#pragma unroll
-		for (int k = 0; k < WBC_ROUNDS; ++k)
-			if (lane + 32 * k < WBC_STATE / 2) reinterpret_cast<double2 *>(S)[lane + 32 * k] = nxt[k];
-		__syncwarp();
-		if (t + stride < limit) wbc_fetch(nxt, state, index ? index[t + stride] : t + stride, lane);
+		const double *S = buf[cur];
 		wbc_emit(out.Ppr + (size_t)r * out.nnzP, sdesc, out.nnzP, S, lane);
 		wbc_emit(out.Apr + (size_t)r * out.nnzA, sdesc + out.nnzP, out.nnzA, S, lane);
 		wbc_emit(out.Gpr + (size_t)r * out.nnzG, sdesc + out.nnzP + out.nnzA, out.nnzG, S, lane);
 		wbc_emit(out.c + (size_t)r * out.n, sdesc + nV, out.n, S, lane);
 		wbc_emit(out.h + (size_t)r * out.m, sdesc + nV + out.n, out.m, S, lane);
 		wbc_emit(out.b + (size_t)r * out.p, sdesc + nV + out.n + out.m, out.p, S, lane);
+		__syncwarp(); // (every lane is done with this buffer before the fetch after next overwrites it)
 	}
 }
 

@@ -236,9 +236,9 @@ qp_int QPB_BATCH_LAST_LAUNCHES(const QPBatch *batch);
  * interpreting the pattern's wave schedules, 1 = throughput kernel (one QP per thread, working sets
  * interleaved in HBM) interpreting the pattern's micro-programs, 2 = the throughput kernel specialised for the
  * pattern (straight-line code, see QPB_PLAN_STREAM_KEY), 3 = the warp-per-QP kernel specialised for the pattern
- * (lane = row of L, factor resident in shared memory).  Dispatch: the throughput kernel takes batches of at
- * least QPB_STREAM_MIN QPs [default 2048; 113,664 = three waves of its lanes where the library carries a
- * specialised warp-per-QP kernel for the pattern], the warp-per-QP kernel everything smaller. */
+ * (lane = row of L, factor resident in shared memory).  Dispatch: where the library carries a specialised warp-per-QP
+ * kernel for the pattern (DogBot stance / trot / crawl) it takes every batch; otherwise the throughput kernel takes
+ * batches of at least QPB_STREAM_MIN QPs [default 2048] and the interpreted warp-per-QP kernel everything smaller. */
 int QPB_BATCH_LAST_KERNEL(const QPBatch *batch);
 
 /* ---------------------------------------------------------------------------------------------
