@@ -775,10 +775,12 @@ static qp_int qp_solve_batch_host(QPBatch *B, qp_int count, const settings *opts
 		CUDA_TRY(cudaStreamWaitEvent(B->copy_stream, B->ev_go, 0));
 		// (the copies are queued BEFORE the launch: a tool that makes launches synchronous must not wait for
 		// a kernel whose input is not even on its way)
+		// (small first chunks: the kernel starts on the first 256 rows while the rest is on its way)
 		const size_t chunk = std::max<size_t>(2048, (n + 63) / 64);
 		int k = 0;
-		for (size_t lo = 0; lo < n; lo += chunk, ++k) {
-			const size_t cnt = std::min(chunk, n - lo);
+		size_t step = 256;
+		for (size_t lo = 0; lo < n; lo += step, step = std::min(chunk, step * 2), ++k) {
+			const size_t cnt = std::min(step, n - lo);
 			for (int i = 0; i < 6; ++i)
 				if (widths[i]) CUDA_TRY(cudaMemcpyAsync(B->d_in[i] + lo * widths[i], src[i] + lo * widths[i], cnt * widths[i] * sizeof(double), cudaMemcpyHostToDevice, B->copy_stream));
 			B->h_marks[k] = (int)(lo + cnt);

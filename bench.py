@@ -206,6 +206,7 @@ def latency_leg(qpswift, dogbot, ticks=1000):
     P, A, G = [np.ascontiguousarray(a) for a in batch.dense_batch()]
     lb = qpswift.lib()
     us, xs, its = np.empty(ticks), np.empty((ticks, pat.n)), np.empty(ticks, dtype=np.int64)
+    kernel_us, setup_us = np.empty(ticks), np.empty(ticks)
     PD = C.POINTER(C.c_double)
     for t in range(-20, ticks):  # (20 untimed ticks: plan cache, first launch)
         i = t % batch.count
@@ -220,9 +221,11 @@ def latency_leg(qpswift, dogbot, ticks=1000):
         t1 = time.perf_counter_ns()
         if t >= 0:
             us[t], xs[t], its[t] = (t1 - t0) * 1e-3, x, qp.contents.stats.contents.IterationCount
+            kernel_us[t], setup_us[t] = qp.contents.stats.contents.kkt_time * 1e6, qp.contents.stats.contents.tsetup * 1e6
         lb.QP_CLEANUP_dense(qp)
     out = {"workload": "configs[0]: one DogBot stance WBC QP per control tick (n30 m68 p18), QP_SETUP_dense -> QP_SOLVE -> x -> QP_CLEANUP_dense, reltol = abstol = 1e-2 (main.cpp:1649-1663)",
-           "ticks": ticks, "unit": "us", "b200": {"p50": float(np.percentile(us, 50)), "p99": float(np.percentile(us, 99)), "mean": float(us.mean())},
+           "ticks": ticks, "unit": "us", "b200": {"p50": float(np.percentile(us, 50)), "p99": float(np.percentile(us, 99)), "mean": float(us.mean()),
+                    "kernel_p50": float(np.percentile(kernel_us, 50)), "setup_p50": float(np.percentile(setup_us, 50)), "iterations_mean": float(its.mean())},
            "budget_us": 2500.0}
     if R.available("reference"):
         ref = R.control_loop(batch, ticks)

@@ -75,3 +75,29 @@ def test_full_size_batch_properties(qps, oracle, monkeypatch, kernel):
     ref = oracle.solve_batch(sample)
     check_against_oracle({k: out[k][pick] for k in ("x", "y", "z", "s", "flag", "iters")}, ref)
     solver.close()
+
+
+@pytest.mark.parametrize("kind,count", [("stance", 32768), ("crawl", 32768), ("mpc", 32768)])
+def test_other_patterns_at_size(qps, oracle, kind, count):
+    """The other BASELINE.json patterns at 32,768 QPs each (configs[2]'s stance and crawl shares on the specialised
+    warp-per-QP kernel; configs[4]'s horizon-10 MPC QP on the interpreted one): qpSWIFT's stop test recomputed on the
+    host for every QP, composition independence, and a spread sample against the oracle."""
+    batch = dogbot.generate_parallel(kind, count)
+    solver = qps.BatchSolver(batch.pattern, count)
+    out = solver.solve(batch)
+    assert solver.last_kernel == "warp" and solver.last_kernel_generated == (kind != "mpc")
+    ok = out["flag"] == qps.QP_OPTIMAL
+    assert ok.all()
+    n_rx, n_ry, n_rz, mu = _residual_norms(batch, out)
+    thr, slack = 1e-6 / np.sqrt(3.0), 1.0 + 1e-6
+    assert (n_rx < thr * slack).all() and (n_ry < thr * slack).all() and (n_rz < thr * slack).all() and (mu < 1e-6 * slack).all()
+    assert (out["s"] > 0).all() and (out["z"] > 0).all()
+    lo, hi = count // 3, count // 3 + 5000
+    part = solver.solve(batch.slice(lo, hi))
+    for k in ("x", "y", "z", "s", "flag", "iters"):
+        assert np.array_equal(part[k], out[k][lo:hi]), k
+    pick = np.linspace(0, count - 1, 128).astype(int)
+    sample = dogbot.Batch(batch.pattern, *[np.ascontiguousarray(getattr(batch, f)[pick]) for f in ("Ppr", "Apr", "Gpr", "c", "h", "b")])
+    ref = oracle.solve_batch(sample)
+    check_against_oracle({k: out[k][pick] for k in ("x", "y", "z", "s", "flag", "iters")}, ref)
+    solver.close()
