@@ -423,6 +423,8 @@ static int launch_fused(QPBatch *B, BatchIO io, const settings *opts, cudaStream
 	prm.sigma0 = opts->sigma;
 	prm.sigma_d = B->sigma_d;
 	prm.spill_after = 0;
+	prm.groups = getenv("QPB_WARP_GROUPS") ? atoi(getenv("QPB_WARP_GROUPS")) : 1;
+	prm.group_delay_ns = getenv("QPB_WARP_GROUP_DELAY") ? (unsigned)atol(getenv("QPB_WARP_GROUP_DELAY")) : 25000u;
 	io.index = nullptr;
 	io.count_ptr = nullptr;
 	io.spill = nullptr;
@@ -628,7 +630,7 @@ qp_int QP_SOLVE_BATCH_DEVICE_INDEXED(QPBatch *B, qp_int rows, const settings *op
 	io.index = dindex; io.count_ptr = dcount_ptr;
 	io.spill = nullptr; io.spill_count = nullptr; io.spill_sigma = nullptr; io.ready = nullptr; io.server_done = nullptr; io.done_ctas = io.all_done = nullptr; io.trace = nullptr;
 	SolveParams prm;
-	prm.maxit = (int)opts->maxit; prm.reltol = opts->reltol; prm.abstol = opts->abstol; prm.sigma0 = opts->sigma; prm.sigma_d = B->sigma_d; prm.spill_after = 0;
+	prm.maxit = (int)opts->maxit; prm.reltol = opts->reltol; prm.abstol = opts->abstol; prm.sigma0 = opts->sigma; prm.sigma_d = B->sigma_d; prm.spill_after = 0; prm.groups = 1; prm.group_delay_ns = 0;
 	cudaStream_t st = (cudaStream_t)stream;
 	CUDA_TRY(cudaMemsetAsync(B->d_counter, 0, sizeof(int), st));
 	B->last_kernel = B->gen_warp ? 3 : 0;

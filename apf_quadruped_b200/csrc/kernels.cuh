@@ -34,6 +34,8 @@ struct SolveParams
 	int maxit;
 	double reltol, abstol, sigma0, sigma_d;
 	int spill_after; // throughput kernel: hand a QP that has not converged after this many iterations to the latency kernel (0: never)
+	int groups;               // warp-per-QP kernel: 1 = the warps of a CTA walk the iteration together, 2 = two halves half a cycle apart
+	unsigned group_delay_ns;
 };
 
 struct BatchIO
