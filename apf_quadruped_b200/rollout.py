@@ -11,10 +11,9 @@ schedule staggered over the robots, APF-perturbed footholds for the swing feet f
 * ``Rollout`` -- the device loop: ``QPB_ROLLOUT_TICK_DEVICE`` + per pattern ``QPB_WBC_FORMULATE_DEVICE`` /
   ``QP_SOLVE_BATCH_DEVICE_INDEXED`` / ``QPB_WBC_TORQUES_DEVICE`` on the pattern's device-side robot list; one tick is
   captured once in a CUDA graph (three branches, one per contact pattern) and replayed.
-* ``reference_rollout`` -- the SAME model stepped in numpy with the CPU oracle solving every QP (cold start, as the
-  reference always does: ``Auxilary.c:992-1089``); the device loop must match it bit for bit, tick by tick
-  (``tests/test_rollout_gpu.py``).  Test infrastructure: it imports ``oracle`` and is only called by tests and by the
-  bench's in-run check.
+* ``tick_reference`` -- the SAME model in numpy, operation for operation.  ``oracle/rollout_reference.py`` (test
+  infrastructure) steps it with the CPU oracle solving every QP (cold start, as the reference always does:
+  ``Auxilary.c:992-1089``); the device loop must match that bit for bit, tick by tick (``tests/test_rollout_gpu.py``).
 * ``bench`` -- the ``rollout`` record of ``bench.py``.
 
 Warm start has no reference semantics (no API for it): the rollout is cold-start, which is what keeps it
@@ -135,33 +134,6 @@ def tick_reference(S, Rw, x, tick: int, first: int = 0, seed: int = DEFAULT_SEED
     return kind
 
 
-def reference_rollout(robots: int, ticks: int, first: int = 0, seed: int = DEFAULT_SEED, reltol=1e-2, abstol=1e-2, record=None):
-    """The rollout on the CPU: the numpy model + the CPU oracle (QP_SETUP + QP_SOLVE per QP, cold start) + the numpy torque
-    restatement.  TEST INFRASTRUCTURE (imports oracle/).  Returns the final (S, Rw, x, tau) and per-tick records."""
-    from oracle import reference as Rf
-    S, Rw = initial(robots, first, seed)
-    x = np.zeros((robots, 30))
-    tau = np.zeros((robots, 12))
-    flags = np.zeros(robots, dtype=np.int64)
-    iters = np.zeros(robots, dtype=np.int64)
-    log = []
-    for t in range(ticks):
-        kind = tick_reference(S, Rw, x, t, first, seed)
-        for k, name in enumerate(KIND_NAMES):
-            idx = np.nonzero(kind == k)[0]
-            if idx.size == 0:
-                continue
-            rows = wbc.value_rows(name, S[idx])
-            ref, _ = Rf.run_batch(rows, reltol=reltol, abstol=abstol)
-            x[idx] = ref["x"]
-            flags[idx], iters[idx] = ref["flag"], ref["iters"]
-            tau[idx] = wbc.torques_reference(name, S[idx], ref["x"])
-        log.append({"kind": kind.copy(), "x": x.copy(), "tau": tau.copy(), "flag": flags.copy(), "iters": iters.copy()})
-        if record is not None:
-            record(t, S, Rw, x, tau)
-    return S, Rw, x, tau, log
-
-
 class Rollout:
     """The device loop for ``robots`` robots on one GPU (robots first .. first+robots-1 of the whole rollout)."""
 
@@ -254,26 +226,15 @@ class Rollout:
         self.legs = []
 
 
-def bench(args, env, torch, dist, opts):
+def bench(args, env, torch, dist, opts, check=None):
     """bench.py's `rollout` record: robots-per-GPU x ticks sequential control ticks on every GPU (weak scaling over the
     robots; nothing crosses GPUs during the ticks), device time by CUDA events, max over ranks; robot-ticks per second
-    = QP solves per second.  Rank 0 checks a 64-robot x 50-tick rollout of its first robots against the CPU oracle
-    stepping the same model, bit for bit, inside the run."""
+    = QP solves per second.  `check` (bench.py passes the CPU-oracle comparison of a 64-robot x 50-tick rollout) runs
+    on rank 0 inside the run."""
     rank, world, local, dev = env
     R, T = int(args.robots_per_gpu), int(args.ticks)
     first = rank * R
-    check = None
-    if rank == 0:
-        small = Rollout(torch, 64, device=local, first=0)
-        small.step(50)
-        got = small.snapshot()
-        small.close()
-        Sr, Rwr, xr, taur, log = reference_rollout(64, 50, first=0)
-        same = bool(np.array_equal(got["x"], xr) and np.array_equal(got["tau"], taur) and np.array_equal(got["S"], Sr) and np.array_equal(got["Rw"], Rwr)
-                    and np.array_equal(got["iters"], log[-1]["iters"]))
-        if not same:
-            raise AssertionError("rollout: the device loop differs from the CPU oracle stepping the same model")
-        check = {"robots": 64, "ticks": 50, "bit_identical_with_cpu_oracle": same, "qp_solves_checked": 64 * 50}
+    checked = check(torch, local) if (check is not None and rank == 0) else None
     ro = Rollout(torch, R, device=local, first=first)
     ro.step(max(3, min(25, T // 10)))  # warm-up ticks (graph capture included)
     torch.cuda.synchronize()
@@ -297,6 +258,6 @@ def bench(args, env, torch, dist, opts):
            "ticks_per_s": T / (ms * 1e-3), "ms_per_tick": ms / T, "gpu_launches": T * ro.launches_per_tick, "cuda_graph": bool(ro.use_graph),
            "not_optimal_last_tick": int((snap["flag"] != 0).sum()), "iterations_mean_last_tick": float(snap["iters"].mean()),
            "warm_start": "none: the reference has no warm-start semantics (Auxilary.c:992-1089 always cold-starts); cold start keeps the loop comparable with the oracle",
-           "oracle_check": check}
+           "oracle_check": checked}
     ro.close()
     return rec

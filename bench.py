@@ -491,7 +491,8 @@ def run_mpc(args, env, torch, dist, qpswift, dogbot, opts):
 def run_rollout(args, env, torch, dist, qpswift, dogbot, opts):
     """configs[3]: robots x sequential control ticks, everything on the device (apf_quadruped_b200/rollout.py)."""
     from apf_quadruped_b200 import rollout
-    return rollout.bench(args, env, torch, dist, opts)
+    from oracle import rollout_reference
+    return rollout.bench(args, env, torch, dist, opts, check=rollout_reference.check_device_rollout)
 
 
 def main():

@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 
 from apf_quadruped_b200 import rollout, wbc
+from oracle import rollout_reference
 
 
 def test_schedule_keeps_all_three_patterns_busy():
@@ -33,12 +34,12 @@ def test_reference_rollout_closes_the_loop():
     if not (R.available("reference") or R.available("port")):
         pytest.skip("no CPU oracle built")
     seen = set()
-    S, Rw, x, tau, log = rollout.reference_rollout(6, 60)
+    S, Rw, x, tau, log = rollout_reference.reference_rollout(6, 60)
     for rec in log:
         assert np.all(rec["flag"] == 0)
         seen |= set(np.unique(rec["kind"]))
     assert seen == {0, 1, 2}
     assert np.all(np.isfinite(S)) and np.all(np.isfinite(tau)) and np.abs(tau).max() <= 60.0 + 1e-6
     assert np.abs(Rw[:, rollout.RR_DX:rollout.RR_DV]).max() < 0.05
-    S2, Rw2, x2, tau2, _ = rollout.reference_rollout(3, 60, first=3)
+    S2, Rw2, x2, tau2, _ = rollout_reference.reference_rollout(3, 60, first=3)
     assert np.array_equal(S[3:], S2) and np.array_equal(x[3:], x2) and np.array_equal(tau[3:], tau2) and np.array_equal(Rw[3:], Rw2)

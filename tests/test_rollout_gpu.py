@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from apf_quadruped_b200 import rollout
+from oracle import rollout_reference
 
 pytestmark = pytest.mark.gpu
 
@@ -23,7 +24,7 @@ def test_device_rollout_matches_the_cpu_oracle_tick_by_tick():
         if t < 3 or t == 26:
             seen[t] = (S.copy(), Rw.copy(), x.copy(), tau.copy())
 
-    S, Rw, x, tau, log = rollout.reference_rollout(64, 50, record=record)
+    S, Rw, x, tau, log = rollout_reference.reference_rollout(64, 50, record=record)
     for t in range(50):
         ro.step(1)
         if t in seen:
