@@ -968,9 +968,10 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
     key = plan.stream_key()
     st = Structure(plan, vglobal)
     progs = (gen_factor(st), gen_solve(st), gen_resid(st))
+    ns = f"genw_{kind}" if vglobal else f"genws_{kind}"  # (throughput variant / latency variant: value row in shared memory)
     out = [f"// GENERATED by apf_quadruped_b200/codegen_warp.py for the '{kind}' pattern (pattern key {key:#018x}); do not edit.",
-           f"// passes: {[(r[0], r[-1]) for r in progs[0].passes]}",
-           '#include "warp_kernel.cuh"', "", "namespace qpb {", f"namespace genw_{kind} {{", ""]
+           f"// passes: {[(r[0], r[-1]) for r in progs[0].passes]}; value row {'in the global scratch row' if vglobal else 'in shared memory'}",
+           '#include "warp_kernel.cuh"', "", "namespace qpb {", f"namespace {ns} {{", ""]
     for ir in progs:
         tabname = f"tab_{ir.name}"
         vals = ", ".join(str(v) for v in ir.tab) or "0"
@@ -983,7 +984,7 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
         clay["V"] = lay["smem"]
     clay["total"] = lay["smem"]
     nv = len(st.pattern.Pir) + len(st.pattern.Air) + len(st.pattern.Gir)
-    max_warps = max(1, min(int(os.environ.get("QPB_GEN_MAX_WARPS", "10")), (227 * 1024) // (lay["smem"] * 8)))
+    max_warps = max(1, min(int(os.environ.get("QPB_GEN_MAX_WARPS", "10")) if vglobal else 8, (227 * 1024) // (lay["smem"] * 8)))
     out += ["struct Prog", "{",
             "\tstatic constexpr bool own_residuals = true;",
             "\tstatic constexpr bool realign = %s; // barriers inside factor / solve need every warp's count" % ("true" if bar else "false"),
@@ -992,12 +993,12 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
             "\tstatic constexpr bool static_shape = true;",
             "\tstatic constexpr int kN = %d, kM = %d, kP = %d, kOffA = %d, kOffG = %d, kNV = %d;" % (st.n, st.m, st.p, len(st.pattern.Pir), len(st.pattern.Pir) + len(st.pattern.Air), nv),
             "\tstatic __device__ __forceinline__ SliceLayout layout() { SliceLayout L; %s return L; }" % " ".join(f"L.{f} = {clay[f]};" for f in LAYOUT_FIELDS),
-            "\tstatic __device__ __forceinline__ void factor(const ProgramView &, const unsigned sb, const unsigned nbar, const char *vb) { genw_%s::factor(sb, nbar, vb); }" % kind,
-            "\tstatic __device__ __forceinline__ void solve(const ProgramView &, const unsigned sb, const unsigned nbar, const char *vb) { genw_%s::solve(sb, nbar, vb); }" % kind,
-            "\tstatic __device__ __forceinline__ void resid(const unsigned sb, const char *vb) { genw_%s::resid(sb, 32u, vb); }" % kind,
-            "};", "", f"}} // namespace genw_{kind}", "",
-            "static const SliceLayout layout_%s = {%s};" % (kind, ", ".join(str(clay[f]) for f in LAYOUT_FIELDS)),
-            f"QPB_REGISTER_GENERATED_WARP({kind}, {key:#018x}ull, layout_{kind}, genw_{kind}::Prog, {max_warps})", "", "} // namespace qpb", ""]
+            "\tstatic __device__ __forceinline__ void factor(const ProgramView &, const unsigned sb, const unsigned nbar, const char *vb) { %s::factor(sb, nbar, vb); }" % ns,
+            "\tstatic __device__ __forceinline__ void solve(const ProgramView &, const unsigned sb, const unsigned nbar, const char *vb) { %s::solve(sb, nbar, vb); }" % ns,
+            "\tstatic __device__ __forceinline__ void resid(const unsigned sb, const char *vb) { %s::resid(sb, 32u, vb); }" % ns,
+            "};", "", f"}} // namespace {ns}", "",
+            "static const SliceLayout layout_%s = {%s};" % (ns, ", ".join(str(clay[f]) for f in LAYOUT_FIELDS)),
+            f"QPB_REGISTER_GENERATED_WARP({ns}, {key:#018x}ull, layout_{ns}, {ns}::Prog, {max_warps})", "", "} // namespace qpb", ""]
     stats = {ir.name: dict(statements=len(ir.st), table=len(ir.tab),
                            **{k: sum(1 for s in ir.st if s[0] == k) for k in ("lds", "sts", "ldt", "msub", "div", "sync", "shfl", "chain")})
              for ir in progs}
@@ -1012,19 +1013,21 @@ def main():
     ap.add_argument("--out", default="build/gen")
     ap.add_argument("--chunk", type=int, default=1500)
     ap.add_argument("--bar", type=int, default=0, help="a CTA barrier about every so many statements of factor / solve (0: none)")
-    ap.add_argument("--vsmem", action="store_true", help="keep the value row P | A | G in shared memory (fewer warps per SM) instead of in the warp's global scratch row")
+    ap.add_argument("--vsmem", action="store_true", help="ONLY the variant that keeps the value row P | A | G in shared memory (default: both variants -- "
+                    "the throughput one with the value row in the warp's global scratch row, and this one for batches that are in flight all at once)")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     for kind in a.kinds:
-        src, stats = generate(kind, a.chunk, a.bar, not a.vsmem)
-        path = os.path.join(a.out, f"warp_gen_{kind}.cu")
-        old = open(path).read() if os.path.exists(path) else None
-        if old != src:
-            with open(path, "w") as f:
-                f.write(src)
-        print(f"{path}:")
-        for seg, s in stats.items():
-            print(f"  {seg}: {s}")
+        for vglobal in ((False,) if a.vsmem else (True, False)):
+            src, stats = generate(kind, a.chunk, a.bar, vglobal)
+            path = os.path.join(a.out, f"warp_gen_{kind}.cu" if vglobal else f"warp_gens_{kind}.cu")
+            old = open(path).read() if os.path.exists(path) else None
+            if old != src:
+                with open(path, "w") as f:
+                    f.write(src)
+            print(f"{path}:")
+            for seg, st_ in stats.items():
+                print(f"  {seg}: {st_}")
 
 
 if __name__ == "__main__":

@@ -66,10 +66,12 @@ void register_generated_warp_kernel(unsigned long long key, const void *kernel, 
 {
 	generated_warp_kernels().push_back(GeneratedWarpKernel{key, kernel, kernel_free, name, lay, max_warps, value_row_doubles});
 }
-const GeneratedWarpKernel *find_generated_warp_kernel(unsigned long long key)
+// Two variants may be registered per pattern: the throughput one (value row in the global scratch row: more warps per
+// SM) and the latency one (whole working set in shared memory: no L2 round trip on a lone warp's critical path).
+const GeneratedWarpKernel *find_generated_warp_kernel(unsigned long long key, bool value_row_global)
 {
 	for (const GeneratedWarpKernel &k : generated_warp_kernels())
-		if (k.key == key) return &k;
+		if (k.key == key && (k.value_row_doubles > 0) == value_row_global) return &k;
 	return nullptr;
 }
 
@@ -172,6 +174,8 @@ struct QPBatch
 	const GeneratedKernel *generated = nullptr; // the pattern's specialised kernel, if the library carries one
 	const GeneratedWarpKernel *gen_warp = nullptr; // the pattern's specialised warp-per-QP kernel, if the library carries one
 	int gen_warps = 0;      // warps per CTA of that kernel
+	const GeneratedWarpKernel *gen_warp_small = nullptr; // ... and its latency variant for batches that are in flight all at once
+	int gen_warps_small = 0;
 	size_t smem_limit = 0;
 	// device staging for the host-pointer entry point
 	double *d_in[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -225,7 +229,10 @@ static int batch_alloc(QPBatch *B)
 	B->max_warps = (int)std::min<size_t>(MAX_WARPS_PER_CTA, B->smem_limit / slice);
 	CUDA_TRY(cudaFuncSetAttribute(qp_solve_warp_kernel<InterpretedWaves, MAX_WARPS_PER_CTA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
 	if (B->sprog.ok && !getenv("QPB_WARP_INTERPRET")) {
-		const GeneratedWarpKernel *g = find_generated_warp_kernel(stream_program_key(B->sprog));
+		const unsigned long long key = stream_program_key(B->sprog);
+		const GeneratedWarpKernel *g = find_generated_warp_kernel(key, true);
+		const GeneratedWarpKernel *gs = find_generated_warp_kernel(key, false);
+		if (!g) { g = gs; gs = nullptr; }
 		if (g) {
 			B->gen_warp = g;
 			B->gen_warps = (int)std::min<size_t>((size_t)g->max_warps, B->smem_limit / ((size_t)g->lay.total * sizeof(double)));
@@ -234,6 +241,12 @@ static int batch_alloc(QPBatch *B)
 			CUDA_TRY(cudaFuncSetAttribute(g->kernel_free, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
 			if (g->value_row_doubles) // one scratch row per warp of the largest grid (+ a tail: lanes beyond a row's end may read past it)
 				CUDA_TRY(cudaMalloc(&B->d_vscratch, ((size_t)B->sm_count * g->max_warps * g->value_row_doubles + 64) * sizeof(double)));
+		}
+		if (gs && !getenv("QPB_WARP_NO_SMALL")) {
+			B->gen_warp_small = gs;
+			B->gen_warps_small = (int)std::min<size_t>((size_t)gs->max_warps, B->smem_limit / ((size_t)gs->lay.total * sizeof(double)));
+			CUDA_TRY(cudaFuncSetAttribute(gs->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
+			CUDA_TRY(cudaFuncSetAttribute(gs->kernel_free, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
 		}
 	}
 	CUDA_TRY(cudaFuncSetAttribute(ldl_numeric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->smem_limit));
@@ -317,21 +330,25 @@ static int batch_alloc_staging(QPBatch *B)
 
 static int launch_latency(QPBatch *B, const BatchIO &io, const SolveParams &prm, long count, int *counter, cudaStream_t st)
 {
-	// one persistent CTA per SM; small batches spread over the SMs with fewer warps per CTA
-	const int most = B->gen_warp ? B->gen_warps : B->max_warps;
+	// one persistent CTA per SM; small batches spread over the SMs with fewer warps per CTA.  A batch that is in flight
+	// all at once (every QP has its warp from the start: control ticks, rollouts) is a matter of LATENCY: it goes to
+	// the variant that keeps the whole working set in shared memory.
+	const GeneratedWarpKernel *gk = B->gen_warp;
+	int most = gk ? B->gen_warps : B->max_warps;
+	if (B->gen_warp_small && !io.server_done && count <= (long)B->sm_count * B->gen_warps_small) { gk = B->gen_warp_small; most = B->gen_warps_small; }
 	long warps = (count + B->sm_count - 1) / B->sm_count;
 	if (warps > most) warps = most;
 	if (warps < 1) warps = 1;
 	long grid = (count + warps - 1) / warps;
 	if (grid > B->sm_count) grid = B->sm_count;
-	const SliceLayout &lay = B->gen_warp ? B->gen_warp->lay : B->program.lay;
+	const SliceLayout &lay = gk ? gk->lay : B->program.lay;
 	const size_t smem = (size_t)warps * lay.total * sizeof(double);
-	if (B->gen_warp) {
+	if (gk) {
 		const int *plan = B->d_plan;
 		BatchIO gio = io;
 		gio.vscratch = B->d_vscratch;
 		void *args[] = {&plan, &B->pview, const_cast<SliceLayout *>(&lay), &gio, const_cast<SolveParams *>(&prm), &counter};
-		CUDA_TRY(cudaLaunchKernel(getenv("QPB_WARP_FREE") && !io.server_done ? B->gen_warp->kernel_free : B->gen_warp->kernel, dim3((unsigned)grid), dim3((unsigned)warps * 32), args, smem, st));
+		CUDA_TRY(cudaLaunchKernel(getenv("QPB_WARP_FREE") && !io.server_done ? gk->kernel_free : gk->kernel, dim3((unsigned)grid), dim3((unsigned)warps * 32), args, smem, st));
 	} else qp_solve_warp_kernel<InterpretedWaves, MAX_WARPS_PER_CTA, true><<<(unsigned)grid, (unsigned)warps * 32, smem, st>>>(B->d_plan, B->pview, B->program.lay, io, prm, counter);
 	CUDA_TRY(cudaGetLastError());
 	return 0;

@@ -43,7 +43,7 @@ struct GeneratedWarpKernel
 };
 
 void register_generated_warp_kernel(unsigned long long key, const void *kernel, const void *kernel_free, const char *name, const SliceLayout &lay, int max_warps, int value_row_doubles);
-const GeneratedWarpKernel *find_generated_warp_kernel(unsigned long long key);
+const GeneratedWarpKernel *find_generated_warp_kernel(unsigned long long key, bool value_row_global);
 
 #ifdef __CUDACC__
 
