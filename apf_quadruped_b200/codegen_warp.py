@@ -204,6 +204,10 @@ class Emulator:
                 k = st[0]
                 if k == "ldt":
                     env[st[1]] = self.tab[st[2] + L]
+                elif k == "ldt2":
+                    w = np.asarray(self.ir.tab32, dtype=np.int64)[st[3] + L]
+                    env[st[1]] = w & 0xffff
+                    env[st[2]] = w >> 16
                 elif k == "lds":
                     a = self._addr(env, st[2], st[3], st[4])
                     for l in range(st[5]):
@@ -538,7 +542,7 @@ def gen_factor(st: Structure, passes=None) -> IR:
             dr = ir.op("regu", d)
             ir.scatter([st.D(k) if k in left else None for k in rows], dr)
         ir.emit("sync")
-    return hoist_v_loads(ir, st)
+    return pack_tables(hoist_v_loads(ir, st))
 
 
 def gen_solve(st: Structure, passes=None) -> IR:
@@ -683,7 +687,7 @@ def gen_solve(st: Structure, passes=None) -> IR:
         v = ir.gather([X(j) for j in js], X(js[0]), tail_any=True)
         ir.scatter([(lay["rhs"] + st.P[j]) * 8 for j in js], v)
     ir.emit("sync")
-    return hoist_v_loads(ir, st)  # (no value-row loads here: the tables of per-lane offsets are requested early)
+    return pack_tables(hoist_v_loads(ir, st))  # (no value-row loads here: the tables of per-lane offsets are requested early)
 
 
 def gen_resid(st: Structure) -> IR:
@@ -746,7 +750,7 @@ def gen_resid(st: Structure) -> IR:
         acc = ir.op("add", acc, ir.op("sub", u, v))
         ir.scatter([o[3] for o in chunk], acc)
     ir.emit("sync")
-    return hoist_v_loads(ir, st)
+    return pack_tables(hoist_v_loads(ir, st))
 
 
 def hoist_v_loads(ir: IR, st: Structure, dist=None, tdist=None):
@@ -759,7 +763,9 @@ def hoist_v_loads(ir: IR, st: Structure, dist=None, tdist=None):
     dist = int(os.environ.get("QPB_GEN_VDIST", "100")) if dist is None else dist
     # the tables of per-lane offsets are global loads too, and with the slices filling shared memory the L1 that would
     # hold them is a few KB: they come from L2, so they are requested early as well
-    tdist = int(os.environ.get("QPB_GEN_TDIST", "60")) if tdist is None else tdist
+    # (60 statements ahead with one table row per load; 30 since two rows come with one load -- pack_tables: 10 / 20 / 30 / 40
+    # measured 1.730 / 1.727 / 1.741 / 1.727 M solves/s on trot)
+    tdist = int(os.environ.get("QPB_GEN_TDIST", "30")) if tdist is None else tdist
     tab_of = {}
     keyed = []
     for idx, s in enumerate(ir.st):
@@ -784,6 +790,35 @@ def hoist_v_loads(ir: IR, st: Structure, dist=None, tdist=None):
     return ir
 
 
+def pack_tables(ir: IR, window=None):
+    """Two table rows per load: an `ldt` and the next one within `window` statements become one `ldt2` that reads a
+    32-bit word per lane (low half = the first row's offset, high half = the second's) from a second, 32-bit table;
+    the rows left single move to a compacted 16-bit table.  Halves the table loads (LSU instructions and wavefronts).
+    The second row is read a few statements earlier than before: the tables are read-only, nothing else changes."""
+    window = int(os.environ.get("QPB_GEN_PACK", "24")) if window is None else window
+    ir.tab32 = []
+    if window <= 0 or any(s[0] == "chain" for s in ir.st):
+        return ir
+    st, out, tab16, second = ir.st, [], [], set()
+    for idx, s in enumerate(st):
+        if idx in second:
+            continue
+        if s[0] != "ldt":
+            out.append(s)
+            continue
+        partner = next((j for j in range(idx + 1, min(len(st), idx + 1 + window)) if st[j][0] == "ldt" and j not in second), None)
+        if partner is None:
+            out.append(("ldt", s[1], len(tab16)))
+            tab16.extend(ir.tab[s[2]:s[2] + NLANE])
+        else:
+            a, b = s[2], st[partner][2]
+            out.append(("ldt2", s[1], st[partner][1], len(ir.tab32)))
+            ir.tab32.extend(ir.tab[a + l] | (ir.tab[b + l] << 16) for l in range(NLANE))
+            second.add(partner)
+    ir.st, ir.tab = out, tab16
+    return ir
+
+
 # ---------------------------------------------------------------------------------------------------
 # CUDA
 # ---------------------------------------------------------------------------------------------------
@@ -801,6 +836,8 @@ def print_function(ir: IR, out, fname, tabname, chunk=1500, bar=0):
         cuts.append(len(sts))
     defined_in = {}
     for idx, s in enumerate(sts):
+        if s[0] == "ldt2":
+            defined_in[s[1]] = defined_in[s[2]] = idx
         if s[0] in ("ldt", "lds", "const", "add0", "msub", "msubp", "mul", "sub", "div", "regu", "shfl", "pne", "prange", "pmask", "selc", "sel", "pnez", "add", "mulc", "chain"):
             defined_in[s[1]] = idx
 
@@ -870,7 +907,7 @@ def print_function(ir: IR, out, fname, tabname, chunk=1500, bar=0):
         return {"d": "double", "i": "unsigned", "p": "bool"}[v[0]]
 
     for name, live_in, live_out, lo, hi in names:
-        args = ["const unsigned sb", "const unsigned sbl", "const unsigned lane", "const unsigned short *__restrict__ tl", "const unsigned nbar", "const char *vb", "const char *vbl"]
+        args = ["const unsigned sb", "const unsigned sbl", "const unsigned lane", "const unsigned short *__restrict__ tl", "const unsigned *__restrict__ tl2", "const unsigned nbar", "const char *vb", "const char *vbl"]
         args += [f"const {ctype(v)} {v}" for v in live_in]
         args += [f"{ctype(v)} &o_{v}" for v in live_out]
         out.append(f"static __device__ __noinline__ void {name}({', '.join(args)})\n{{")
@@ -891,6 +928,8 @@ def print_function(ir: IR, out, fname, tabname, chunk=1500, bar=0):
                 continue
             if k == "ldt":
                 out.append(f"\tconst unsigned {s[1]} = __ldg(tl + {s[2]});")
+            elif k == "ldt2":
+                out.append(f"\tconst unsigned w{s[1]} = __ldg(tl2 + {s[3]}); const unsigned {s[1]} = w{s[1]} & 0xffffu, {s[2]} = w{s[1]} >> 16;")
             elif k == "lds" and s[1] in vloads:
                 # the value row: global memory (the warp's scratch row; vb is pre-offset so that slice offsets apply), L2 only
                 base = "vbl" if s[4] else "vb"
@@ -951,14 +990,14 @@ def print_function(ir: IR, out, fname, tabname, chunk=1500, bar=0):
             out.append(f"\to_{v} = {v};")
         out.append("}\n")
     out.append(f"static __device__ __forceinline__ void {fname}(const unsigned sb, const unsigned nbar, const char *vb)\n{{")
-    out.append(f"\tconst unsigned lane = threadIdx.x & 31u, sbl = sb + 8u * lane;\n\tconst unsigned short *tl = {tabname} + lane;\n\tconst char *vbl = vb + 8u * lane;")
+    out.append(f"\tconst unsigned lane = threadIdx.x & 31u, sbl = sb + 8u * lane;\n\tconst unsigned short *tl = {tabname} + lane;\n\tconst unsigned *tl2 = {tabname}32 + lane;\n\tconst char *vbl = vb + 8u * lane;")
     declared = set()
     for name, live_in, live_out, lo, hi in names:
         for v in live_out:
             if v not in declared:
                 out.append(f"\t{ctype(v)} {v};")
                 declared.add(v)
-        out.append(f"\t{name}({', '.join(['sb', 'sbl', 'lane', 'tl', 'nbar', 'vb', 'vbl'] + live_in + live_out)});")
+        out.append(f"\t{name}({', '.join(['sb', 'sbl', 'lane', 'tl', 'tl2', 'nbar', 'vb', 'vbl'] + live_in + live_out)});")
     out.append("}\n")
 
 
@@ -976,6 +1015,8 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
         tabname = f"tab_{ir.name}"
         vals = ", ".join(str(v) for v in ir.tab) or "0"
         out.append(f"__device__ const unsigned short {tabname}[] = {{{vals}}};\n")
+        vals32 = ", ".join(f"{v}u" for v in getattr(ir, "tab32", [])) or "0u"
+        out.append(f"__device__ const unsigned {tabname}32[] = {{{vals32}}};\n")
         print_function(ir, out, ir.name, tabname, chunk, bar if ir.name != "resid" else 0)
     lay = st.lay
     # what the kernel gets: the shared-memory part of the slice (V outside it: in the warp's global scratch row)
@@ -999,8 +1040,8 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
             "};", "", f"}} // namespace {ns}", "",
             "static const SliceLayout layout_%s = {%s};" % (ns, ", ".join(str(clay[f]) for f in LAYOUT_FIELDS)),
             f"QPB_REGISTER_GENERATED_WARP({ns}, {key:#018x}ull, layout_{ns}, {ns}::Prog, {max_warps})", "", "} // namespace qpb", ""]
-    stats = {ir.name: dict(statements=len(ir.st), table=len(ir.tab),
-                           **{k: sum(1 for s in ir.st if s[0] == k) for k in ("lds", "sts", "ldt", "msub", "div", "sync", "shfl", "chain")})
+    stats = {ir.name: dict(statements=len(ir.st), table=len(ir.tab), table32=len(getattr(ir, "tab32", [])),
+                           **{k: sum(1 for s in ir.st if s[0] == k) for k in ("lds", "sts", "ldt", "ldt2", "msub", "div", "sync", "shfl", "chain")})
              for ir in progs}
     stats["layout"] = dict(smem=st.lay["smem"], bytes=st.lay["smem"] * 8, tsize=st.lay["tsize"], value_row_global=lay["vglobal"], nV=nv, max_warps=max_warps)
     plan.close()

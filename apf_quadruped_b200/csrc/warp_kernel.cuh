@@ -89,6 +89,59 @@ __device__ __forceinline__ unsigned group_count(const SyncGroup g, const bool pr
 }
 __device__ __forceinline__ bool group_or(const SyncGroup g, const bool pred) { return group_count(g, pred) != 0; }
 
+// One QP's rows P | A | G | c | h | b for a program that knows its sizes at compile time: all loads are issued before the
+// first store (a loop of load -> store pairs would pay one trip to HBM per pass, because the compiler must keep a store
+// to the scratch row in global memory ahead of the next load), coalesced 8-byte requests, 256 bytes per warp each.
+template <int COUNT, bool L2_ONLY>
+struct RowInFlight
+{
+	static constexpr int K = COUNT > 0 ? (COUNT + 31) / 32 : 1;
+	double v[K];
+	__device__ __forceinline__ void load(const double *__restrict__ src, const int lane)
+	{
+#pragma unroll
+		for (int k = 0; k < K; ++k) {
+			const int i = lane + 32 * k;
+			v[k] = 0.0;
+			if (i < COUNT) v[k] = L2_ONLY ? __ldcg(src + i) : __ldg(src + i);
+		}
+	}
+	template <bool PLUS_ZERO>
+	__device__ __forceinline__ void store(double *dst, const int lane) const
+	{
+#pragma unroll
+		for (int k = 0; k < K; ++k) {
+			const int i = lane + 32 * k;
+			if (i < COUNT) dst[i] = PLUS_ZERO ? v[k] + 0.0 : v[k];
+		}
+	}
+};
+
+template <class PROG, bool L2_ONLY>
+__device__ __forceinline__ void load_qp_static(const WarpState &w, const BatchIO &io, const size_t qi)
+{
+	constexpr int nP = PROG::kOffA, nA = PROG::kOffG - PROG::kOffA, nG = PROG::kNV - PROG::kOffG;
+	const int lane = lane_id();
+	RowInFlight<nP, L2_ONLY> rP;
+	RowInFlight<nA, L2_ONLY> rA;
+	RowInFlight<nG, L2_ONLY> rG;
+	RowInFlight<PROG::kN, L2_ONLY> rc;
+	RowInFlight<PROG::kM, L2_ONLY> rh;
+	RowInFlight<PROG::kP, L2_ONLY> rb;
+	rP.load(io.Ppr + qi * nP, lane);
+	if (nA) rA.load(io.Apr + qi * nA, lane);
+	rG.load(io.Gpr + qi * nG, lane);
+	rc.load(io.c + qi * PROG::kN, lane);
+	rh.load(io.h + qi * PROG::kM, lane);
+	if (PROG::kP) rb.load(io.b + qi * PROG::kP, lane);
+	rP.template store<true>(w.V, lane);
+	if (nA) rA.template store<true>(w.V + nP, lane);
+	rG.template store<true>(w.V + PROG::kOffG, lane);
+	rc.template store<false>(w.c, lane);
+	rh.template store<false>(w.h, lane);
+	if (PROG::kP) rb.template store<false>(w.b, lane);
+}
+
 struct InterpretedWaves
 {
 	static constexpr bool own_residuals = false;
@@ -133,11 +186,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 	const double thr = prm.reltol / sqrt(3.0);
 
 	SyncGroup grp = {0u, blockDim.x};
-	if (CTA_SYNC && prm.groups == 2 && blockDim.x >= 128) {
-		const unsigned nw = blockDim.x >> 5, first = (nw + 1) >> 1;
-		grp.id = (unsigned)warp < first ? 1u : 2u;
-		grp.threads = 32u * ((unsigned)warp < first ? first : nw - first);
-		if (grp.id == 2u) __nanosleep(prm.group_delay_ns); // half a cycle behind the first half
+	if (CTA_SYNC && prm.groups >= 2 && prm.groups <= 8 && blockDim.x >= 32u * (unsigned)prm.groups) {
+		// group g = warps [g nw / G, (g + 1) nw / G): named barrier g + 1, started g * delay behind the first group
+		const unsigned nw = blockDim.x >> 5, G = (unsigned)prm.groups;
+		unsigned g = 0;
+		while ((g + 1) * nw / G <= (unsigned)warp) ++g;
+		grp.id = g + 1u;
+		grp.threads = 32u * ((g + 1) * nw / G - g * nw / G);
+		for (unsigned t = 0; t < g; ++t) __nanosleep(prm.group_delay_ns);
 	}
 	int q = 0, iters = 0;
 	bool active = false; // a QP is between its initial point and its exit
@@ -228,7 +284,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 					__syncwarp();
 				}
 				// matrix values as v + 0.0 (-0.0 becomes +0.0): what "Y[i] += value" from Y[i] == 0 makes of them (ldl.c:284)
-				if (io.ready) { // (rows that arrive while the kernel runs: L2 only)
+				if (PROG::static_shape) { // every load of the QP's six rows in flight before the first store: ONE round trip to HBM
+					if (io.ready) load_qp_static<PROG, true>(w, io, qi);
+					else load_qp_static<PROG, false>(w, io, qi);
+				} else if (io.ready) { // (rows that arrive while the kernel runs: L2 only)
 					warp_copy_in<true, true>(w.V, io.Ppr + qi * pv.offA, pv.offA);
 					if (p) warp_copy_in<true, true>(w.V + pv.offA, io.Apr + qi * (pv.offG - pv.offA), pv.offG - pv.offA);
 					warp_copy_in<true, true>(w.V + pv.offG, io.Gpr + qi * (pv.nV - pv.offG), pv.nV - pv.offG);

@@ -29,6 +29,11 @@ VARIANTS = {
     "warp9": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_WARPS": "9"},
     "warp10": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_WARPS": "10"},
     "warp11": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_WARPS": "11"},
+    # the warps of a CTA in G groups that run 1/G of a cycle apart (QPB_WARP_GROUP_DELAY: ns between two groups' starts)
+    "warp_g2": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_GROUPS": "2", "QPB_WARP_GROUP_DELAY": "25000"},
+    "warp_g3": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_GROUPS": "3", "QPB_WARP_GROUP_DELAY": "17000"},
+    "warp_g4": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_GROUPS": "4", "QPB_WARP_GROUP_DELAY": "13000"},
+    "warp_g6": {"QPB_STREAM_MIN": "1000000000", "QPB_WARP_GROUPS": "6", "QPB_WARP_GROUP_DELAY": "9000"},
 }
 
 
@@ -52,7 +57,7 @@ def main():
     ptr = lambda t: t.data_ptr() if t.numel() else None
     results = {}
     for name in a.variants:
-        for k in ("QPB_STREAM_MIN", "QPB_WARP_INTERPRET", "QPB_WARP_FREE", "QPB_WARP_WARPS"):
+        for k in ("QPB_STREAM_MIN", "QPB_WARP_INTERPRET", "QPB_WARP_FREE", "QPB_WARP_WARPS", "QPB_WARP_GROUPS", "QPB_WARP_GROUP_DELAY"):
             os.environ.pop(k, None)
         os.environ.update(VARIANTS[name])
         os.environ.update(dict(e.split("=", 1) for e in a.env))
