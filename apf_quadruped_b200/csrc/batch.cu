@@ -449,7 +449,6 @@ static int launch_fused(QPBatch *B, BatchIO io, const settings *opts, cudaStream
 	io.spill_sigma = nullptr;
 	io.server_done = nullptr;
 	io.done_ctas = io.all_done = nullptr;
-	if (!(B->d_workspace && io.count >= B->stream_min) && !B->gen_warp) io.ready = nullptr; // (the interpreted warp-per-QP kernel takes whole batches only)
 	CUDA_TRY(cudaMemsetAsync(B->d_counter, 0, sizeof(int), st));
 	if (B->d_workspace && io.count >= B->stream_min) return launch_stream(B, io, prm, st);
 	B->last_kernel = B->gen_warp ? 3 : 0;
@@ -763,8 +762,8 @@ static qp_int qp_solve_batch_host(QPBatch *B, qp_int count, const settings *opts
 	// device's address space): the throughput kernel writes a finished QP's rows 256 bytes at a time over the
 	// bus while the others are still being solved, instead of one copy of everything after the kernel.
 	bool direct[4] = {false, false, false, false};
-	// (both the throughput kernel and the specialised warp-per-QP kernel take QPs in index order from a queue)
-	const bool overlap = ((B->d_workspace && count >= B->stream_min) || (B->gen_warp && count >= 4096)) && !getenv("QPB_NO_OVERLAP");
+	// (the throughput kernel and the warp-per-QP kernels, generated or interpreted, take QPs in index order from a queue)
+	const bool overlap = ((B->d_workspace && count >= B->stream_min) || count >= 4096) && !getenv("QPB_NO_OVERLAP");
 	if (overlap) {
 		qp_real *host_out[4] = {x, y, z, s};
 		double **dev_out[4] = {&io.x, &io.y, &io.z, &io.s};
