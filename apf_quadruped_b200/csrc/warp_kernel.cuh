@@ -73,9 +73,9 @@ __device__ __forceinline__ double lane_chain(double acc, const unsigned sb, cons
 	return acc;
 }
 
-// The warps of a CTA that walk the iteration together: the whole CTA (barrier 0), or -- QPB_WARP_GROUPS=2, an experiment --
-// one of two halves (named barriers 1 and 2) that run half a cycle apart, so that the LSU-heavy and the FP64-heavy
-// phases of the two halves overlap instead of colliding (measured: +0.8 % on trot; the default stays one group).
+// The warps of a CTA that walk the iteration together: the whole CTA (barrier 0), or -- QPB_WARP_GROUPS=G, an experiment --
+// one of G groups (named barriers 1..G) that run 1/G of a cycle apart, so that the LSU-heavy and the FP64-heavy
+// phases of the groups overlap instead of colliding (measured: erratic, -40 % to +2 % on trot; the default stays one group).
 struct SyncGroup
 {
 	unsigned id, threads;
