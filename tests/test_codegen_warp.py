@@ -134,3 +134,37 @@ def test_layout_fits_more_warps_than_the_interpreted_one(qps):
         assert st.lay["smem"] < st.lay["total"] < full["total"] and st.lay["tsize"] >= 2 * plan.pattern.m
         assert st.lay["V"] >= st.lay["smem"], "the value row lies outside the shared-memory part of the slice"
         assert all(st.lay[k] % 2 == 0 for k in W.LAYOUT_FIELDS if k not in ("total", "tsize"))
+
+
+def test_table_rows_are_read_two_per_load(qps, monkeypatch):
+    """pack_tables: two `ldt` within the window become one `ldt2` over a 32-bit table whose halves are the two rows'
+    16-bit offsets; the rows left single move to a compacted 16-bit table; the programs see the same offsets."""
+    plan = qps.Plan(dogbot.generate("trot", 1).pattern)
+    st = W.Structure(plan)
+    monkeypatch.setenv("QPB_GEN_PACK", "0")
+    plain = W.gen_solve(st)
+    monkeypatch.setenv("QPB_GEN_PACK", "24")
+    packed = W.gen_solve(st)
+    assert not plain.tab32 and not any(s[0] == "ldt2" for s in plain.st)
+    singles = [s for s in packed.st if s[0] == "ldt"]
+    pairs = [s for s in packed.st if s[0] == "ldt2"]
+    loads_before = sum(1 for s in plain.st if s[0] == "ldt")
+    assert pairs and len(singles) + 2 * len(pairs) == loads_before and len(singles) + len(pairs) < 0.6 * loads_before
+    assert len(packed.tab) == 32 * len(singles) and len(packed.tab32) == 32 * len(pairs)
+    # every variable keeps its row of offsets
+    rows_plain = {s[1]: tuple(plain.tab[s[2]:s[2] + 32]) for s in plain.st if s[0] == "ldt"}
+    rows_packed = {s[1]: tuple(packed.tab[s[2]:s[2] + 32]) for s in singles}
+    for s in pairs:
+        words = packed.tab32[s[3]:s[3] + 32]
+        rows_packed[s[1]] = tuple(w & 0xffff for w in words)
+        rows_packed[s[2]] = tuple(w >> 16 for w in words)
+    assert rows_packed == rows_plain
+    # a variable is still defined before its first use
+    seen = set()
+    for s in packed.st:
+        if s[0] == "ldt":
+            seen.add(s[1])
+        elif s[0] == "ldt2":
+            seen.update(s[1:3])
+        elif s[0] == "lds" and s[2] is not None:
+            assert s[2] in seen
