@@ -297,7 +297,7 @@ class Emulator:
 LAYOUT_FIELDS = ["zero", "V", "c", "h", "b", "zd", "Lx", "D", "T", "rhs", "x", "y", "z", "s", "r", "lam", "ds", "dz", "dsl", "total", "tsize"]
 
 
-def compact_layout(n, m, p, N, nV, lnz, vglobal=True):
+def compact_layout(n, m, p, N, nV, lnz, vglobal=True, vsize=None):
     """SliceLayout (csrc/program.h) with the scratch area T cut down to what the generated programs use: the
     permuted work vector of the solves (N) and the products of one column of the backward sweep (64); the
     kernel's own scratch (-(P x): n, rho's products: 2m) fits in the same doubles.
@@ -325,13 +325,48 @@ def compact_layout(n, m, p, N, nV, lnz, vglobal=True):
         take(name, cnt)
     lay["smem"] = at
     if vglobal:
-        take("V", nV)
+        take("V", nV if vsize is None else vsize)  # (vsize: the row in residual order, Structure.vslots)
         take("vzero", 2)
     else:
         lay["vzero"] = lay["zero"]
     lay["total"] = at
     lay["vglobal"] = bool(vglobal)
     return lay
+
+
+def resid_chains(pat):
+    """computeresiduals' sparse products (Auxilary.c:753-785) as the chains gen_resid runs, one output row per lane:
+    a list of groups (the rows of one chain() call), each a list of per-lane term lists [(value index into P | A | G,
+    vector name, vector index), ...] in the reference's order -- column scatter delivers a row's terms in ascending
+    column order, column gather a column's terms in storage order.  Groups: per 32 rows of rx [P x] then [G'z + A'y];
+    then per 32 rows of ry | rz [A x or G x]."""
+    n, m, p = pat.n, pat.m, pat.p
+    nnzP, nnzA = len(pat.Pir), len(pat.Air)
+
+    def rows_of(jc, ir_, nrows, voff, vec):
+        out = [[] for _ in range(nrows)]
+        for col in range(len(jc) - 1):
+            for q in range(int(jc[col]), int(jc[col + 1])):
+                out[int(ir_[q])].append((voff + q, vec, col))
+        return out
+
+    def cols_of(jc, ir_, voff, vec):
+        return [[(voff + q, vec, int(ir_[q])) for q in range(int(jc[col]), int(jc[col + 1]))] for col in range(len(jc) - 1)]
+
+    Px = rows_of(pat.Pjc, pat.Pir, n, 0, "x")
+    Gtz = cols_of(pat.Gjc, pat.Gir, nnzP + nnzA, "z")
+    Aty = cols_of(pat.Ajc, pat.Air, nnzP, "y") if p else [[] for _ in range(n)]
+    Ax = rows_of(pat.Ajc, pat.Air, p, nnzP, "x") if p else []
+    Gx = rows_of(pat.Gjc, pat.Gir, m, nnzP + nnzA, "x")
+    groups = []
+    for w0 in range(0, n, NLANE):
+        rows = list(range(w0, min(n, w0 + NLANE)))
+        groups.append([Px[i] for i in rows])
+        groups.append([Gtz[i] + Aty[i] for i in rows])
+    outs = Ax + Gx
+    for w0 in range(0, len(outs), NLANE):
+        groups.append(outs[w0:w0 + NLANE])
+    return groups
 
 
 class Structure:
@@ -341,7 +376,26 @@ class Structure:
         sl = info["layout"]
         self.N = N = plan.info("N")
         pat0 = plan.pattern
-        self.lay = compact_layout(pat0.n, pat0.m, pat0.p, N, len(pat0.Pir) + len(pat0.Air) + len(pat0.Gir), plan.info("lnz"), vglobal)
+        nV0 = len(pat0.Pir) + len(pat0.Air) + len(pat0.Gir)
+        # Value row in the global scratch row: laid out in RESIDUAL ORDER -- slot 32 T + lane holds the value that lane
+        # multiplies at step T of the residual products (resid_chains), +0.0 where the lane has no term -- so that the
+        # residuals read it with coalesced loads at constant addresses instead of table-driven gathers.  A value that two
+        # products use (A and G: A x and A'y, G x and G'z) has two slots; the factorisation reads the first.
+        self.resid_groups = resid_chains(pat0)
+        self.vslots = None
+        vsize = None
+        if vglobal and int(os.environ.get("QPB_GEN_RESID_ORDER", "1")):
+            self.vslots = [[] for _ in range(nV0)]
+            T = 0
+            for grp in self.resid_groups:
+                for t in range(max((len(tl) for tl in grp), default=0)):
+                    for lane, tl in enumerate(grp):
+                        if t < len(tl):
+                            self.vslots[tl[t][0]].append(NLANE * T + lane)
+                    T += 1
+            assert all(1 <= len(v) <= 2 for v in self.vslots), "a value the residual products never read (or read more than twice)"
+            vsize = NLANE * T
+        self.lay = compact_layout(pat0.n, pat0.m, pat0.p, N, nV0, plan.info("lnz"), vglobal, vsize)
         lay = self.lay
         self.Lp = [int(v) for v in plan.array("Lp")]
         self.Li = [int(v) for v in plan.array("Li")]
@@ -361,7 +415,7 @@ class Structure:
             if e == sl["zero"]:
                 return None
             if sl["V"] <= e < sl["V"] + nV:
-                return (lay["V"] + e - sl["V"]) * 8
+                return (lay["V"] + (self.vslots[e - sl["V"]][0] if self.vslots else e - sl["V"])) * 8
             assert sl["zd"] <= e < sl["zd"] + self.m, "KKT entry that is neither a matrix value nor the (z,z) diagonal"
             return (lay["zd"] + e - sl["zd"]) * 8
 
@@ -394,6 +448,18 @@ class Structure:
 
     def col(self, j):
         return [(self.Li[q], q) for q in range(self.Lp[j], self.Lp[j + 1])]
+
+    def place_values(self, S, vals):
+        """The value row P | A | G (as v + 0.0) where the programs expect it in the slice S: in storage order, or -- value
+        row in the scratch row -- in residual order with +0.0 in the slots without a term (what the kernel does on load)."""
+        lay = self.lay
+        if self.vslots is None:
+            S[lay["V"]:lay["V"] + len(vals)] = np.asarray(vals) + 0.0
+            return
+        S[lay["V"]:lay["vzero"]] = 0.0
+        for v, slots in zip(vals, self.vslots):
+            for sl_ in slots:
+                S[lay["V"] + sl_] = v + 0.0
 
     def in_v(self, off):
         """Is the byte offset in the value row's address space (global scratch row) rather than in shared memory?"""
@@ -699,52 +765,43 @@ def gen_resid(st: Structure) -> IR:
     lay, ZERO = st.lay, st.ZERO
     pat = st.pattern
     n, m, p = st.n, st.m, st.p
-    nnzP, nnzA = len(pat.Pir), len(pat.Air)
     B = lambda name, i: (lay[name] + i) * 8
-
-    def rows_of(jc, ir_, nrows, voff, vec):
-        out = [[] for _ in range(nrows)]
-        for col in range(len(jc) - 1):
-            for q in range(int(jc[col]), int(jc[col + 1])):
-                out[int(ir_[q])].append((B("V", voff + q), B(vec, col)))
-        return out
-
-    def cols_of(jc, ir_, voff, vec):
-        return [[(B("V", voff + q), B(vec, int(ir_[q]))) for q in range(int(jc[col]), int(jc[col + 1]))] for col in range(len(jc) - 1)]
-
-    Px = rows_of(pat.Pjc, pat.Pir, n, 0, "x")
-    Gtz = cols_of(pat.Gjc, pat.Gir, nnzP + nnzA, "z")
-    Aty = cols_of(pat.Ajc, pat.Air, nnzP, "y") if p else [[] for _ in range(n)]
-    Ax = rows_of(pat.Ajc, pat.Air, p, nnzP, "x") if p else []
-    Gx = rows_of(pat.Gjc, pat.Gir, m, nnzP + nnzA, "x")
+    groups = iter(st.resid_groups)
     tmp = lay["T"]  # scratch: -(P x), read by the kernel's sums
     zero = ir.d()
     ir.emit("const", zero, 0.0)
+    step = [0]  # steps of the residual products so far: row 32 T of the value row in residual order
 
-    def chain(acc, terms_per_lane):
+    def chain(acc, grp):
         """acc -= V[a_t] * S[b_t], t ascending, per lane.  Value row in shared memory: one table-driven loop.  Value row
-        in global memory: unrolled, so that the loads of V can be issued far ahead of their use (hoist_v_loads)."""
+        in global memory: unrolled, so that the loads of V can be issued far ahead of their use (hoist_v_loads); in
+        residual order they are coalesced loads at constant addresses."""
+        terms_per_lane = [[(B("V", v), B(vec, i)) for v, vec, i in tl] for tl in grp]
         if not st.lay["vglobal"]:
             return ir.chain(acc, terms_per_lane, ZERO)
         for t in range(max((len(tl) for tl in terms_per_lane), default=0)):
-            a = ir.gather([tl[t][0] if t < len(tl) else None for tl in terms_per_lane], st.VZERO)
+            if st.vslots is not None:
+                a = ir.lds(None, B("V", NLANE * step[0]), 1)
+                step[0] += 1
+            else:
+                a = ir.gather([tl[t][0] if t < len(tl) else None for tl in terms_per_lane], st.VZERO)
             b = ir.gather([tl[t][1] if t < len(tl) else None for tl in terms_per_lane], ZERO)
             acc = ir.op("msub", acc, a, b)  # (a padded term is acc - (+0)(+0): no accumulator here is ever -0.0)
         return acc
 
     for w0 in range(0, n, NLANE):
         rows = list(range(w0, min(n, w0 + NLANE)))
-        acc = chain(zero, [Px[i] for i in rows])
+        acc = chain(zero, next(groups))
         ir.scatter([(tmp + i) * 8 for i in rows], acc)
-        acc = chain(acc, [Gtz[i] + Aty[i] for i in rows])
+        acc = chain(acc, next(groups))
         cv = ir.gather([B("c", i) for i in rows], ZERO)
         acc = ir.op("add", acc, ir.op("mulc", cv, -1.0))  # rx[i] += c[i] * (-1)
         ir.scatter([B("r", i) for i in rows], acc)
     # ry and rz rows share waves: r[n + i] = acc + (u - v) with (u, v) = (b, +0.0) for ry (b - 0 = b*1 exactly), (h, s) for rz
-    outs = [(Ax[i], B("b", i), None, B("r", n + i)) for i in range(p)] + [(Gx[i], B("h", i), B("s", i), B("r", n + p + i)) for i in range(m)]
+    outs = [(None, B("b", i), None, B("r", n + i)) for i in range(p)] + [(None, B("h", i), B("s", i), B("r", n + p + i)) for i in range(m)]
     for w0 in range(0, len(outs), NLANE):
         chunk = outs[w0:w0 + NLANE]
-        acc = chain(zero, [o[0] for o in chunk])
+        acc = chain(zero, next(groups))
         u = ir.gather([o[1] for o in chunk], ZERO)
         v = ir.gather([o[2] for o in chunk], ZERO)
         acc = ir.op("add", acc, ir.op("sub", u, v))
@@ -1011,6 +1068,10 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
     out = [f"// GENERATED by apf_quadruped_b200/codegen_warp.py for the '{kind}' pattern (pattern key {key:#018x}); do not edit.",
            f"// passes: {[(r[0], r[-1]) for r in progs[0].passes]}; value row {'in the global scratch row' if vglobal else 'in shared memory'}",
            '#include "warp_kernel.cuh"', "", "namespace qpb {", f"namespace {ns} {{", ""]
+    if st.vslots is not None:  # where the kernel puts a QP's values: first and second slot of every entry of P | A | G
+        dst = [v[0] for v in st.vslots] + [v[1] if len(v) > 1 else 0xffff for v in st.vslots]
+        assert max(v for v in dst if v != 0xffff) < 0xffff
+        out.append(f"__device__ const unsigned short vdst[] = {{{', '.join(str(v) for v in dst)}}};\n")
     for ir in progs:
         tabname = f"tab_{ir.name}"
         vals = ", ".join(str(v) for v in ir.tab) or "0"
@@ -1030,7 +1091,9 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
             "\tstatic constexpr bool own_residuals = true;",
             "\tstatic constexpr bool realign = %s; // barriers inside factor / solve need every warp's count" % ("true" if bar else "false"),
             "\tstatic constexpr bool value_row_global = %s; // V = P | A | G in the warp's scratch row in global memory, not in the slice" % ("true" if lay["vglobal"] else "false"),
-            "\tstatic constexpr int value_row_doubles = %d; // nV + the zero behind it, padded" % (lay["total"] - lay["smem"] if lay["vglobal"] else 0),
+            "\tstatic constexpr int value_row_doubles = %d; // the row + the zero behind it, padded" % (lay["total"] - lay["smem"] if lay["vglobal"] else 0),
+            "\tstatic constexpr bool value_row_resid_order = %s; // the row holds the values in the order of the residual products (slots: vdst)" % ("true" if st.vslots is not None else "false"),
+            "\tstatic __device__ __forceinline__ unsigned vdst(const int i) { return %s; }" % (f"__ldg({ns}::vdst + i)" if st.vslots is not None else "0u"),
             "\tstatic constexpr bool static_shape = true;",
             "\tstatic constexpr int kN = %d, kM = %d, kP = %d, kOffA = %d, kOffG = %d, kNV = %d;" % (st.n, st.m, st.p, len(st.pattern.Pir), len(st.pattern.Pir) + len(st.pattern.Air), nv),
             "\tstatic __device__ __forceinline__ SliceLayout layout() { SliceLayout L; %s return L; }" % " ".join(f"L.{f} = {clay[f]};" for f in LAYOUT_FIELDS),
@@ -1043,7 +1106,8 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
     stats = {ir.name: dict(statements=len(ir.st), table=len(ir.tab), table32=len(getattr(ir, "tab32", [])),
                            **{k: sum(1 for s in ir.st if s[0] == k) for k in ("lds", "sts", "ldt", "ldt2", "msub", "div", "sync", "shfl", "chain")})
              for ir in progs}
-    stats["layout"] = dict(smem=st.lay["smem"], bytes=st.lay["smem"] * 8, tsize=st.lay["tsize"], value_row_global=lay["vglobal"], nV=nv, max_warps=max_warps)
+    stats["layout"] = dict(smem=st.lay["smem"], bytes=st.lay["smem"] * 8, tsize=st.lay["tsize"], value_row_global=lay["vglobal"], nV=nv, max_warps=max_warps,
+                           value_row_doubles=lay["total"] - lay["smem"] if lay["vglobal"] else 0, resid_order=st.vslots is not None)
     plan.close()
     return "\n".join(out), stats
 

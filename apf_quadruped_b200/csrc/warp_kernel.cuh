@@ -115,6 +115,24 @@ struct RowInFlight
 			if (i < COUNT) dst[i] = PLUS_ZERO ? v[k] + 0.0 : v[k];
 		}
 	}
+	// entries [first, first + COUNT) of P | A | G to their slots of a value row in residual order (one or two each), as v + 0.0
+	template <class PROG>
+	__device__ __forceinline__ void place(double *row, const int first, const int lane) const
+	{
+		unsigned d1[K], d2[K];
+#pragma unroll
+		for (int k = 0; k < K; ++k) {
+			const int i = lane + 32 * k;
+			d1[k] = d2[k] = 0xffffu;
+			if (i < COUNT) { d1[k] = PROG::vdst(first + i); d2[k] = PROG::vdst(PROG::kNV + first + i); }
+		}
+#pragma unroll
+		for (int k = 0; k < K; ++k) {
+			const double t = v[k] + 0.0;
+			if (d1[k] != 0xffffu) row[d1[k]] = t;
+			if (d2[k] != 0xffffu) row[d2[k]] = t;
+		}
+	}
 };
 
 template <class PROG, bool L2_ONLY>
@@ -134,9 +152,15 @@ __device__ __forceinline__ void load_qp_static(const WarpState &w, const BatchIO
 	rc.load(io.c + qi * PROG::kN, lane);
 	rh.load(io.h + qi * PROG::kM, lane);
 	if (PROG::kP) rb.load(io.b + qi * PROG::kP, lane);
-	rP.template store<true>(w.V, lane);
-	if (nA) rA.template store<true>(w.V + nP, lane);
-	rG.template store<true>(w.V + PROG::kOffG, lane);
+	if (PROG::value_row_resid_order) {
+		rP.template place<PROG>(w.V, 0, lane);
+		if (nA) rA.template place<PROG>(w.V, nP, lane);
+		rG.template place<PROG>(w.V, PROG::kOffG, lane);
+	} else {
+		rP.template store<true>(w.V, lane);
+		if (nA) rA.template store<true>(w.V + nP, lane);
+		rG.template store<true>(w.V + PROG::kOffG, lane);
+	}
 	rc.template store<false>(w.c, lane);
 	rh.template store<false>(w.h, lane);
 	if (PROG::kP) rb.template store<false>(w.b, lane);
@@ -148,6 +172,8 @@ struct InterpretedWaves
 	static constexpr bool realign = true;
 	static constexpr bool value_row_global = false;
 	static constexpr int value_row_doubles = 0;
+	static constexpr bool value_row_resid_order = false;
+	static __device__ __forceinline__ unsigned vdst(const int) { return 0u; }
 	static constexpr bool static_shape = false; // sizes and layout come with the launch
 	static constexpr int kN = 0, kM = 0, kP = 0, kOffA = 0, kOffG = 0, kNV = 0;
 	static __device__ __forceinline__ SliceLayout layout() { return SliceLayout(); }
@@ -179,7 +205,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 		double *vrow = io.vscratch + ((size_t)blockIdx.x * MAXW + warp) * PROG::value_row_doubles;
 		w.V = vrow;
 		vb = reinterpret_cast<const char *>(vrow) - (size_t)lay.V * sizeof(double);
-		if (lane == 0) { vrow[PROG::value_row_doubles - 2] = 0.0; vrow[PROG::value_row_doubles - 1] = 0.0; } // the zero behind the row
+		if (PROG::value_row_resid_order) { // the slots without a term hold +0.0 for good: a QP's values only ever go to their own slots
+			for (int i = lane; i < PROG::value_row_doubles; i += 32) vrow[i] = 0.0;
+		} else if (lane == 0) { vrow[PROG::value_row_doubles - 2] = 0.0; vrow[PROG::value_row_doubles - 1] = 0.0; } // the zero behind the row
 	}
 	__syncwarp();
 	const int n = pv.n, m = pv.m, p = pv.p;
@@ -343,7 +371,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 			PROG::solve(pg, sb, busy, vb);
 		}
 		if (mode == MODE_INIT) {
-			ipm_init_point(pv, w);
+			ipm_init_point(pv, w, [](const int e) { return PROG::value_row_resid_order ? (int)PROG::vdst(e) : e; });
 			active = true;
 		} else if (mode == MODE_PRED) { // affine step length, sigma, corrector right-hand side (qpSWIFT.c:564-570)
 			ipm_recover_and_steplength(n, m, p, w, ap, ad);

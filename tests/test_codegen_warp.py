@@ -11,14 +11,17 @@ from apf_quadruped_b200 import codegen_warp as W
 from apf_quadruped_b200 import dogbot
 
 
-def make_slice(lay, batch, i):
+def make_slice(lay, batch, i, st=None):
     pat = batch.pattern
     S = np.full(lay["total"], np.nan)
     S[lay["zero"]] = 0.0
     S[lay["zero"] + 1] = -0.0
     S[lay["vzero"]] = 0.0  # (the zero behind the value row, in the value row's address space)
     vals = np.concatenate([batch.Ppr[i], batch.Apr[i], batch.Gpr[i]])
-    S[lay["V"]:lay["V"] + vals.size] = vals + 0.0  # (the kernel normalises -0.0 to +0.0 when it loads the values)
+    if st is not None:
+        st.place_values(S, vals)  # (storage order, or residual order for a value row in the scratch row)
+    else:
+        S[lay["V"]:lay["V"] + vals.size] = vals + 0.0  # (the kernel normalises -0.0 to +0.0 when it loads the values)
     S[lay["c"]:lay["c"] + pat.n] = batch.c[i]
     S[lay["h"]:lay["h"] + pat.m] = batch.h[i]
     S[lay["b"]:lay["b"] + pat.p] = batch.b[i]
@@ -71,7 +74,7 @@ def test_generated_warp_programs_reproduce_the_reference(qps, oracle, kind, vglo
     assert all(len(rows) <= 32 for rows in fac.passes) and sorted(k for rows in fac.passes for k in rows) == st.R
     N, lnz, n, m, p = plan.info("N"), plan.info("lnz"), pat.n, pat.m, pat.p
     for i in range(batch.count):
-        S = make_slice(lay, batch, i)
+        S = make_slice(lay, batch, i, st)
         ref = oracle.solve_sparse(pat, batch.Ppr[i], batch.Apr[i], batch.Gpr[i], batch.c[i], batch.h[i], batch.b[i],
                                   maxit=0, want_factor=True)
         W.Emulator(fac, S).run()
@@ -99,7 +102,7 @@ def test_zero_right_hand_side_takes_the_exact_quotient(qps, oracle):
     st = W.Structure(plan)
     fac, sol = W.gen_factor(st), W.gen_solve(st)
     lay, N = st.lay, plan.info("N")
-    S = make_slice(lay, batch, 0)
+    S = make_slice(lay, batch, 0, st)
     W.Emulator(fac, S).run()
     rhs = np.zeros(N)
     rhs[::3] = -0.0
@@ -131,7 +134,7 @@ def test_layout_fits_more_warps_than_the_interpreted_one(qps):
         plan = qps.Plan(dogbot.generate(kind, 1).pattern)
         st = W.Structure(plan)
         full = plan.layout()
-        assert st.lay["smem"] < st.lay["total"] < full["total"] and st.lay["tsize"] >= 2 * plan.pattern.m
+        assert st.lay["smem"] < st.lay["total"] and st.lay["smem"] < full["total"] - plan.pattern.nnzG and st.lay["tsize"] >= 2 * plan.pattern.m
         assert st.lay["V"] >= st.lay["smem"], "the value row lies outside the shared-memory part of the slice"
         assert all(st.lay[k] % 2 == 0 for k in W.LAYOUT_FIELDS if k not in ("total", "tsize"))
 
