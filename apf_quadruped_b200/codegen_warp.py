@@ -141,9 +141,10 @@ class IR:
         has_s = any(o is not None and not v for o, v in zip(offsets, inv))
         if not has_v:
             return self.gather(offsets, st.ZERO)
+        row = st.frow([o if v else None for o, v in zip(offsets, inv)])
         if not has_s:
-            return self.gather(offsets, st.VZERO)
-        gv = self.gather([o if v else None for o, v in zip(offsets, inv)], st.VZERO)
+            return self.gather(offsets, st.VZERO) if row is None else self.lds(None, row, 1)
+        gv = self.gather([o if v else None for o, v in zip(offsets, inv)], st.VZERO) if row is None else self.lds(None, row, 1)
         gs = self.gather([None if v else o for o, v in zip(offsets, inv)], st.ZERO)
         p = self.p()
         self.emit("pmask", p, sum(1 << l for l, v in enumerate(inv) if v))
@@ -369,8 +370,11 @@ def resid_chains(pat):
     return groups
 
 
+FROW_BUDGET = {"trot": 55}  # factor-order rows per pattern (see Structure)
+
+
 class Structure:
-    def __init__(self, plan, vglobal=True):
+    def __init__(self, plan, vglobal=True, frow_budget=0):
         info = plan.stream_info()
         assert info["ok"] == 1
         sl = info["layout"]
@@ -397,6 +401,15 @@ class Structure:
             vsize = NLANE * T
         self.lay = compact_layout(pat0.n, pat0.m, pat0.p, N, nV0, plan.info("lnz"), vglobal, vsize)
         lay = self.lay
+        # ... and the gathers of the factorisation (a pivot row's K entries, a leaf column's entries by row) get rows of their
+        # own BEHIND the value row, 32 slots each in lane order: a third and fourth copy of an entry, coalesced as well
+        # -- as long as the scratch rows of all warps in flight stay well inside L2.  Measured on B200 (65,536 QPs, M solves/s;
+        # rows: 0 / 20 / 40 / 55 / 70 / 90 / all): trot (131 gathers) 1.840 / 1.858 / 1.872 / 1.882 / 1.887 / 1.855 / 1.595,
+        # stance 1.601 / 1.488 / 1.398 / - / 1.404 / - / 0.950, crawl 1.661 / 1.657 / 1.611 / - / 1.503 / - / 0.991: the budget is
+        # a property of the pattern (frow_budget: rows for trot, none for the others; QPB_GEN_FROWS overrides); gathers beyond
+        # it stay table-driven gathers into the residual-order slots.
+        self.frows, self.frow_of, self.F0 = [], {}, lay["total"]
+        self.frow_budget = int(os.environ.get("QPB_GEN_FROWS", str(frow_budget))) if self.vslots is not None else 0
         self.Lp = [int(v) for v in plan.array("Lp")]
         self.Li = [int(v) for v in plan.array("Li")]
         self.P = [int(v) for v in plan.array("P")]
@@ -449,6 +462,30 @@ class Structure:
     def col(self, j):
         return [(self.Li[q], q) for q in range(self.Lp[j], self.Lp[j + 1])]
 
+    def frow(self, offsets):
+        """Byte offset of the factor-order row that holds, in lane order, the value-row entries at `offsets` (None: +0.0);
+        None when there are no such rows (value row in shared memory or in storage order, budget used up)."""
+        if not self.frow_budget:
+            return None
+        first = {self.lay["V"] * 8 + 8 * sl_[0]: e for e, sl_ in enumerate(self.vslots)}
+        key = tuple(None if o is None else first[o] for o in offsets) + (None,) * (NLANE - len(offsets))
+        if key not in self.frow_of:
+            if len(self.frows) >= self.frow_budget:
+                return None
+            self.frow_of[key] = len(self.frows)
+            self.frows.append(key)
+            self.lay["total"] += NLANE
+        return (self.F0 + NLANE * self.frow_of[key]) * 8
+
+    def value_slots(self):
+        """Per entry of P | A | G: its slots in the scratch row (doubles from the row's start): residual order first."""
+        out = [list(v) for v in self.vslots]
+        for r, key in enumerate(self.frows):
+            for lane, e in enumerate(key):
+                if e is not None:
+                    out[e].append(self.F0 - self.lay["V"] + NLANE * r + lane)
+        return out
+
     def place_values(self, S, vals):
         """The value row P | A | G (as v + 0.0) where the programs expect it in the slice S: in storage order, or -- value
         row in the scratch row -- in residual order with +0.0 in the slots without a term (what the kernel does on load)."""
@@ -456,8 +493,8 @@ class Structure:
         if self.vslots is None:
             S[lay["V"]:lay["V"] + len(vals)] = np.asarray(vals) + 0.0
             return
-        S[lay["V"]:lay["vzero"]] = 0.0
-        for v, slots in zip(vals, self.vslots):
+        S[lay["V"]:lay["total"]] = 0.0
+        for v, slots in zip(vals, self.value_slots()):
             for sl_ in slots:
                 S[lay["V"] + sl_] = v + 0.0
 
@@ -1062,14 +1099,16 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
     from . import dogbot, qpswift as Q
     plan = Q.Plan(dogbot.generate(kind, 1).pattern)
     key = plan.stream_key()
-    st = Structure(plan, vglobal)
+    st = Structure(plan, vglobal, FROW_BUDGET.get(kind, 0))
     progs = (gen_factor(st), gen_solve(st), gen_resid(st))
     ns = f"genw_{kind}" if vglobal else f"genws_{kind}"  # (throughput variant / latency variant: value row in shared memory)
     out = [f"// GENERATED by apf_quadruped_b200/codegen_warp.py for the '{kind}' pattern (pattern key {key:#018x}); do not edit.",
            f"// passes: {[(r[0], r[-1]) for r in progs[0].passes]}; value row {'in the global scratch row' if vglobal else 'in shared memory'}",
            '#include "warp_kernel.cuh"', "", "namespace qpb {", f"namespace {ns} {{", ""]
     if st.vslots is not None:  # where the kernel puts a QP's values: first and second slot of every entry of P | A | G
-        dst = [v[0] for v in st.vslots] + [v[1] if len(v) > 1 else 0xffff for v in st.vslots]
+        slots = st.value_slots()
+        kdst = max(len(v) for v in slots)
+        dst = [v[k] if k < len(v) else 0xffff for k in range(kdst) for v in slots]
         assert max(v for v in dst if v != 0xffff) < 0xffff
         out.append(f"__device__ const unsigned short vdst[] = {{{', '.join(str(v) for v in dst)}}};\n")
     for ir in progs:
@@ -1093,6 +1132,7 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
             "\tstatic constexpr bool value_row_global = %s; // V = P | A | G in the warp's scratch row in global memory, not in the slice" % ("true" if lay["vglobal"] else "false"),
             "\tstatic constexpr int value_row_doubles = %d; // the row + the zero behind it, padded" % (lay["total"] - lay["smem"] if lay["vglobal"] else 0),
             "\tstatic constexpr bool value_row_resid_order = %s; // the row holds the values in the order of the residual products (slots: vdst)" % ("true" if st.vslots is not None else "false"),
+            "\tstatic constexpr int kVDst = %d; // slots per entry of P | A | G (vdst[k * kNV + e], 0xffff: none)" % (max(len(v) for v in st.value_slots()) if st.vslots is not None else 0),
             "\tstatic __device__ __forceinline__ unsigned vdst(const int i) { return %s; }" % (f"__ldg({ns}::vdst + i)" if st.vslots is not None else "0u"),
             "\tstatic constexpr bool static_shape = true;",
             "\tstatic constexpr int kN = %d, kM = %d, kP = %d, kOffA = %d, kOffG = %d, kNV = %d;" % (st.n, st.m, st.p, len(st.pattern.Pir), len(st.pattern.Pir) + len(st.pattern.Air), nv),
@@ -1107,7 +1147,7 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
                            **{k: sum(1 for s in ir.st if s[0] == k) for k in ("lds", "sts", "ldt", "ldt2", "msub", "div", "sync", "shfl", "chain")})
              for ir in progs}
     stats["layout"] = dict(smem=st.lay["smem"], bytes=st.lay["smem"] * 8, tsize=st.lay["tsize"], value_row_global=lay["vglobal"], nV=nv, max_warps=max_warps,
-                           value_row_doubles=lay["total"] - lay["smem"] if lay["vglobal"] else 0, resid_order=st.vslots is not None)
+                           value_row_doubles=lay["total"] - lay["smem"] if lay["vglobal"] else 0, resid_order=st.vslots is not None, factor_rows=len(st.frows))
     plan.close()
     return "\n".join(out), stats
 

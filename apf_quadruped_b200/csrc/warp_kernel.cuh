@@ -115,22 +115,20 @@ struct RowInFlight
 			if (i < COUNT) dst[i] = PLUS_ZERO ? v[k] + 0.0 : v[k];
 		}
 	}
-	// entries [first, first + COUNT) of P | A | G to their slots of a value row in residual order (one or two each), as v + 0.0
+	// entries [first, first + COUNT) of P | A | G to their slots of a value row in residual order (PROG::kVDst at most each), as v + 0.0
 	template <class PROG>
 	__device__ __forceinline__ void place(double *row, const int first, const int lane) const
 	{
-		unsigned d1[K], d2[K];
 #pragma unroll
 		for (int k = 0; k < K; ++k) {
 			const int i = lane + 32 * k;
-			d1[k] = d2[k] = 0xffffu;
-			if (i < COUNT) { d1[k] = PROG::vdst(first + i); d2[k] = PROG::vdst(PROG::kNV + first + i); }
-		}
+			unsigned d[PROG::kVDst > 0 ? PROG::kVDst : 1];
 #pragma unroll
-		for (int k = 0; k < K; ++k) {
+			for (int c = 0; c < PROG::kVDst; ++c) d[c] = i < COUNT ? PROG::vdst(c * PROG::kNV + first + i) : 0xffffu;
 			const double t = v[k] + 0.0;
-			if (d1[k] != 0xffffu) row[d1[k]] = t;
-			if (d2[k] != 0xffffu) row[d2[k]] = t;
+#pragma unroll
+			for (int c = 0; c < PROG::kVDst; ++c)
+				if (d[c] != 0xffffu) row[d[c]] = t;
 		}
 	}
 };
@@ -173,6 +171,7 @@ struct InterpretedWaves
 	static constexpr bool value_row_global = false;
 	static constexpr int value_row_doubles = 0;
 	static constexpr bool value_row_resid_order = false;
+	static constexpr int kVDst = 0;
 	static __device__ __forceinline__ unsigned vdst(const int) { return 0u; }
 	static constexpr bool static_shape = false; // sizes and layout come with the launch
 	static constexpr int kN = 0, kM = 0, kP = 0, kOffA = 0, kOffG = 0, kNV = 0;

@@ -58,17 +58,18 @@ def residual_products(pat, Ppr, Apr, Gpr, c, h, b, x, y, z, s):
     return np.concatenate([rx, ry, rz]), px
 
 
-@pytest.mark.parametrize("kind,vglobal", [("trot", True), ("stance", True), ("crawl", True), ("trot", False)])
-def test_generated_warp_programs_reproduce_the_reference(qps, oracle, kind, vglobal):
+@pytest.mark.parametrize("kind,vglobal,frows", [("trot", True, 55), ("stance", True, 0), ("crawl", True, 200), ("trot", False, 0)])
+def test_generated_warp_programs_reproduce_the_reference(qps, oracle, kind, vglobal, frows):
     """vglobal: the value row P | A | G lies outside the shared-memory part of the slice (the warp's scratch row in global
     memory; loads hoisted far ahead of their use) -- the default; False: the whole working set in shared memory."""
     batch = dogbot.generate(kind, 2, start=321)
     pat = batch.pattern
     plan = qps.Plan(pat)
-    st = W.Structure(plan, vglobal)
+    st = W.Structure(plan, vglobal, frows)  # (frows: the factorisation's value gathers with rows of their own behind the value row)
     assert (st.lay["V"] >= st.lay["smem"]) == vglobal
     fac, sol, res = W.gen_factor(st), W.gen_solve(st), W.gen_resid(st)
     lay = st.lay
+    assert len(st.frows) == (min(frows, len(st.frows)) if vglobal else 0) and (len(st.frows) > 0) == (vglobal and frows > 0)
     if vglobal:  # no statement mixes the two address spaces, and every value-row load is marked for the printer
         assert fac.vloads and res.vloads and not sol.vloads
     assert all(len(rows) <= 32 for rows in fac.passes) and sorted(k for rows in fac.passes for k in rows) == st.R
