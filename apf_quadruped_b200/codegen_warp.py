@@ -370,7 +370,7 @@ def resid_chains(pat):
     return groups
 
 
-FROW_BUDGET = {"trot": 55}  # factor-order rows per pattern (see Structure)
+FROW_BUDGET = {}  # factor-order rows per pattern (see Structure): none by default
 
 
 class Structure:
@@ -406,8 +406,9 @@ class Structure:
         # -- as long as the scratch rows of all warps in flight stay well inside L2.  Measured on B200 (65,536 QPs, M solves/s;
         # rows: 0 / 20 / 40 / 55 / 70 / 90 / all): trot (131 gathers) 1.840 / 1.858 / 1.872 / 1.882 / 1.887 / 1.855 / 1.595,
         # stance 1.601 / 1.488 / 1.398 / - / 1.404 / - / 0.950, crawl 1.661 / 1.657 / 1.611 / - / 1.503 / - / 0.991: the budget is
-        # a property of the pattern (frow_budget: rows for trot, none for the others; QPB_GEN_FROWS overrides); gathers beyond
-        # it stay table-driven gathers into the residual-order slots.
+        # a property of the pattern AND of the warps per SM -- with the 12 warps per SM that trot runs since its loads became
+        # cheap (below), rows 0 / 30 / 55: 2.047 / 2.004 / 2.032 -- so there are none by default (frow_budget, FROW_BUDGET;
+        # QPB_GEN_FROWS overrides); gathers beyond the budget stay table-driven gathers into the residual-order slots.
         self.frows, self.frow_of, self.F0 = [], {}, lay["total"]
         self.frow_budget = int(os.environ.get("QPB_GEN_FROWS", str(frow_budget))) if self.vslots is not None else 0
         self.Lp = [int(v) for v in plan.array("Lp")]
@@ -1111,6 +1112,15 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
         dst = [v[k] if k < len(v) else 0xffff for k in range(kdst) for v in slots]
         assert max(v for v in dst if v != 0xffff) < 0xffff
         out.append(f"__device__ const unsigned short vdst[] = {{{', '.join(str(v) for v in dst)}}};\n")
+        # the entries of G by rows (ascending column inside a row: the plan's grow lists, symbolic.cpp) -> a slot each: the
+        # initial point's h - G x (kernels.cuh ipm_init_point) reads the value row through it
+        pat = st.pattern
+        nnzPA = len(pat.Pir) + len(pat.Air)
+        grow = [[] for _ in range(st.m)]
+        for col in range(len(pat.Gjc) - 1):
+            for q in range(int(pat.Gjc[col]), int(pat.Gjc[col + 1])):
+                grow[int(pat.Gir[q])].append(slots[nnzPA + q][0])
+        out.append(f"__device__ const unsigned short gslot[] = {{{', '.join(str(v) for r in grow for v in r)}}};\n")
     for ir in progs:
         tabname = f"tab_{ir.name}"
         vals = ", ".join(str(v) for v in ir.tab) or "0"
@@ -1125,7 +1135,10 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
         clay["V"] = lay["smem"]
     clay["total"] = lay["smem"]
     nv = len(st.pattern.Pir) + len(st.pattern.Air) + len(st.pattern.Gir)
-    max_warps = max(1, min(int(os.environ.get("QPB_GEN_MAX_WARPS", "10")) if vglobal else 8, (227 * 1024) // (lay["smem"] * 8)))
+    # warps per CTA: as many slices as fit, at most 12 (168 registers each).  Until the table loads were halved and the value
+    # row went into residual order, the LSU / MIO queues saturated at 10 warps (11 / 12: no gain); since then trot
+    # 10 / 11 / 12 warps: 1.904 / 2.021 / 2.047 M solves/s (stance: 9 and crawl: 10 slices fit anyway)
+    max_warps = max(1, min(int(os.environ.get("QPB_GEN_MAX_WARPS", "12")) if vglobal else 8, (227 * 1024) // (lay["smem"] * 8)))
     out += ["struct Prog", "{",
             "\tstatic constexpr bool own_residuals = true;",
             "\tstatic constexpr bool realign = %s; // barriers inside factor / solve need every warp's count" % ("true" if bar else "false"),
@@ -1134,6 +1147,7 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
             "\tstatic constexpr bool value_row_resid_order = %s; // the row holds the values in the order of the residual products (slots: vdst)" % ("true" if st.vslots is not None else "false"),
             "\tstatic constexpr int kVDst = %d; // slots per entry of P | A | G (vdst[k * kNV + e], 0xffff: none)" % (max(len(v) for v in st.value_slots()) if st.vslots is not None else 0),
             "\tstatic __device__ __forceinline__ unsigned vdst(const int i) { return %s; }" % (f"__ldg({ns}::vdst + i)" if st.vslots is not None else "0u"),
+            "\tstatic __device__ __forceinline__ unsigned gslot(const int t) { return %s; }" % (f"__ldg({ns}::gslot + t)" if st.vslots is not None else "0u"),
             "\tstatic constexpr bool static_shape = true;",
             "\tstatic constexpr int kN = %d, kM = %d, kP = %d, kOffA = %d, kOffG = %d, kNV = %d;" % (st.n, st.m, st.p, len(st.pattern.Pir), len(st.pattern.Pir) + len(st.pattern.Air), nv),
             "\tstatic __device__ __forceinline__ SliceLayout layout() { SliceLayout L; %s return L; }" % " ".join(f"L.{f} = {clay[f]};" for f in LAYOUT_FIELDS),

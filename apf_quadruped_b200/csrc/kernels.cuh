@@ -414,7 +414,8 @@ __device__ __forceinline__ void ipm_init_rhs(const PlanView &pv, WarpState &w)
 
 // kkt_initialize, second half (Auxilary.c:1044-1083): x, y from the solution, r = h - G x,
 // s and z shifted into the cone.
-// VSLOT(e): where entry e of P | A | G sits in w.V (identity, or its slot of a value row kept in residual order).
+// VSLOT(t, pv): where the t-th entry of G by rows (the plan's grow lists) sits in w.V: pv.grow_val[t], or its slot of a
+// value row kept in residual order.
 template <class VSLOT>
 __device__ __forceinline__ void ipm_init_point(const PlanView &pv, WarpState &w, const VSLOT vslot)
 {
@@ -428,7 +429,7 @@ __device__ __forceinline__ void ipm_init_point(const PlanView &pv, WarpState &w,
 	double *zi = w.dz; // scratch
 	for (int i = lane; i < m; i += 32) {
 		double acc = 0.0;
-		for (int t = __ldg(pv.grow_ptr + i); t < __ldg(pv.grow_ptr + i + 1); ++t) acc -= w.x[__ldg(pv.grow_col + t)] * w.V[vslot(__ldg(pv.grow_val + t))];
+		for (int t = __ldg(pv.grow_ptr + i); t < __ldg(pv.grow_ptr + i + 1); ++t) acc -= w.x[__ldg(pv.grow_col + t)] * w.V[vslot(t, pv)];
 		acc += w.h[i] * 1.0;
 		zi[i] = acc;
 		if (first) { lo = hi = acc; first = false; }

@@ -173,6 +173,7 @@ struct InterpretedWaves
 	static constexpr bool value_row_resid_order = false;
 	static constexpr int kVDst = 0;
 	static __device__ __forceinline__ unsigned vdst(const int) { return 0u; }
+	static __device__ __forceinline__ unsigned gslot(const int) { return 0u; }
 	static constexpr bool static_shape = false; // sizes and layout come with the launch
 	static constexpr int kN = 0, kM = 0, kP = 0, kOffA = 0, kOffG = 0, kNV = 0;
 	static __device__ __forceinline__ SliceLayout layout() { return SliceLayout(); }
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) qp_solve_warp_kernel(const int *
 			PROG::solve(pg, sb, busy, vb);
 		}
 		if (mode == MODE_INIT) {
-			ipm_init_point(pv, w, [](const int e) { return PROG::value_row_resid_order ? (int)PROG::vdst(e) : e; });
+			ipm_init_point(pv, w, [](const int t, const PlanView &v) { return PROG::value_row_resid_order ? (int)PROG::gslot(t) : __ldg(v.grow_val + t); });
 			active = true;
 		} else if (mode == MODE_PRED) { // affine step length, sigma, corrector right-hand side (qpSWIFT.c:564-570)
 			ipm_recover_and_steplength(n, m, p, w, ap, ad);
