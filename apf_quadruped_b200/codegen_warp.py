@@ -298,7 +298,7 @@ class Emulator:
 LAYOUT_FIELDS = ["zero", "V", "c", "h", "b", "zd", "Lx", "D", "T", "rhs", "x", "y", "z", "s", "r", "lam", "ds", "dz", "dsl", "total", "tsize"]
 
 
-def compact_layout(n, m, p, N, nV, lnz, vglobal=True, vsize=None):
+def compact_layout(n, m, p, N, nV, lnz, vglobal=True, vsize=None, pbsize=64):
     """SliceLayout (csrc/program.h) with the scratch area T cut down to what the generated programs use: the
     permuted work vector of the solves (N) and the products of one column of the backward sweep (64); the
     kernel's own scratch (-(P x): n, rho's products: 2m) fits in the same doubles.
@@ -320,7 +320,8 @@ def compact_layout(n, m, p, N, nV, lnz, vglobal=True, vsize=None):
     head = (("V", nV),) if not vglobal else ()
     for name, cnt in head + (("c", n), ("h", m), ("b", p), ("zd", m), ("Lx", lnz), ("D", N)):
         take(name, cnt)
-    lay["tsize"] = max(even(N) + 64, even(2 * m), even(n))
+    lay["pbsize"] = even(pbsize)  # (the products of one column of the backward sweep: gen_solve)
+    lay["tsize"] = max(even(N) + lay["pbsize"], even(2 * m), even(n))
     take("T", lay["tsize"])
     for name, cnt in (("rhs", N), ("x", n), ("y", p), ("z", m), ("s", m), ("r", N), ("lam", max(m, n)), ("ds", m), ("dz", m), ("dsl", m)):
         take(name, cnt)
@@ -374,7 +375,7 @@ FROW_BUDGET = {}  # factor-order rows per pattern (see Structure): none by defau
 
 
 class Structure:
-    def __init__(self, plan, vglobal=True, frow_budget=0):
+    def __init__(self, plan, vglobal=True, frow_budget=0, pbsize=64):
         info = plan.stream_info()
         assert info["ok"] == 1
         sl = info["layout"]
@@ -399,7 +400,7 @@ class Structure:
                     T += 1
             assert all(1 <= len(v) <= 2 for v in self.vslots), "a value the residual products never read (or read more than twice)"
             vsize = NLANE * T
-        self.lay = compact_layout(pat0.n, pat0.m, pat0.p, N, nV0, plan.info("lnz"), vglobal, vsize)
+        self.lay = compact_layout(pat0.n, pat0.m, pat0.p, N, nV0, plan.info("lnz"), vglobal, vsize, pbsize)
         lay = self.lay
         # ... and the gathers of the factorisation (a pivot row's K entries, a leaf column's entries by row) get rows of their
         # own BEHIND the value row, 32 slots each in lane order: a third and fourth copy of an entry, coalesced as well
@@ -654,7 +655,7 @@ def gen_solve(st: Structure, passes=None) -> IR:
     lay, ZERO, N = st.lay, st.ZERO, st.N
     Xs = lay["T"] * 8                 # the permuted work vector w[N]
     PB = (lay["T"] + N + (N & 1)) * 8  # products of one column of the backward sweep
-    assert N + (N & 1) + 64 <= lay["tsize"], "scratch too small"
+    assert N + (N & 1) + lay["pbsize"] <= lay["tsize"], "scratch too small"
     X = lambda j: Xs + 8 * j
     passes = passes or split_passes(st)
     # ---- LDL_perm: w[j] = b[P[j]] -------------------------------------------------------------------
@@ -763,6 +764,7 @@ def gen_solve(st: Structure, passes=None) -> IR:
     ir.emit("sync")
     for j in reversed([c for c in nonleaf if c not in lane_last]):  # earlier passes: products through shared memory
         ent = st.col(j)
+        assert len(ent) <= lay["pbsize"], "product buffer too small (Structure pbsize)"
         acc = ir.lds(None, X(j), 0)  # (read before the sync below: every lane stores the sum back over it)
         for r0 in range(0, len(ent), NLANE):
             chunk = ent[r0:r0 + NLANE]
@@ -1101,6 +1103,15 @@ def generate(kind: str, chunk=1500, bar=0, vglobal=True):
     plan = Q.Plan(dogbot.generate(kind, 1).pattern)
     key = plan.stream_key()
     st = Structure(plan, vglobal, FROW_BUDGET.get(kind, 0))
+    if vglobal:
+        # One more slice per CTA where a product buffer of the size the pattern needs (instead of 64 doubles) makes room for
+        # it: crawl 10 -> 11 warps (2,660 -> 2,638 doubles per slice; 11 slices of 2,641 fit).
+        fits = lambda doubles: min(int(os.environ.get("QPB_GEN_MAX_WARPS", "12")), (227 * 1024) // (doubles * 8))
+        last = set(split_passes(st)[-1])
+        need = max([len(st.col(j)) for j in st.R if st.Lp[j] < st.Lp[j + 1] and j not in last], default=0)
+        slim = compact_layout(st.n, st.m, st.p, st.N, 0, st.lnz, True, 0, need)
+        if fits(slim["smem"]) > fits(st.lay["smem"]) and int(os.environ.get("QPB_GEN_SLIM", "1")):
+            st = Structure(plan, vglobal, FROW_BUDGET.get(kind, 0), need)
     progs = (gen_factor(st), gen_solve(st), gen_resid(st))
     ns = f"genw_{kind}" if vglobal else f"genws_{kind}"  # (throughput variant / latency variant: value row in shared memory)
     out = [f"// GENERATED by apf_quadruped_b200/codegen_warp.py for the '{kind}' pattern (pattern key {key:#018x}); do not edit.",

@@ -58,14 +58,16 @@ def residual_products(pat, Ppr, Apr, Gpr, c, h, b, x, y, z, s):
     return np.concatenate([rx, ry, rz]), px
 
 
-@pytest.mark.parametrize("kind,vglobal,frows", [("trot", True, 0), ("stance", True, 40), ("crawl", True, 200), ("trot", False, 0)])
-def test_generated_warp_programs_reproduce_the_reference(qps, oracle, kind, vglobal, frows):
+@pytest.mark.parametrize("kind,vglobal,frows,pbsize", [("trot", True, 0, 64), ("stance", True, 40, 64), ("crawl", True, 200, 64), ("crawl", True, 0, 42), ("trot", False, 0, 64)])
+def test_generated_warp_programs_reproduce_the_reference(qps, oracle, kind, vglobal, frows, pbsize):
     """vglobal: the value row P | A | G lies outside the shared-memory part of the slice (the warp's scratch row in global
     memory; loads hoisted far ahead of their use) -- the default; False: the whole working set in shared memory."""
     batch = dogbot.generate(kind, 2, start=321)
     pat = batch.pattern
     plan = qps.Plan(pat)
-    st = W.Structure(plan, vglobal, frows)  # (frows: the factorisation's value gathers with rows of their own behind the value row)
+    # frows: the factorisation's value gathers with rows of their own behind the value row; pbsize: the backward sweep's
+    # product buffer (42 doubles is what crawl needs -- and what lets an 11th slice fit, codegen_warp.generate)
+    st = W.Structure(plan, vglobal, frows, pbsize)
     assert (st.lay["V"] >= st.lay["smem"]) == vglobal
     fac, sol, res = W.gen_factor(st), W.gen_solve(st), W.gen_resid(st)
     lay = st.lay
