@@ -174,3 +174,43 @@ def test_table_rows_are_read_two_per_load(qps, monkeypatch):
             seen.update(s[1:3])
         elif s[0] == "lds" and s[2] is not None:
             assert s[2] in seen
+
+
+@pytest.mark.parametrize("kind", ["trot", "stance", "crawl"])
+def test_value_row_in_residual_order(qps, kind):
+    """Structure.vslots: every entry of P | A | G has one slot per product of computeresiduals that reads it (P: 1, A and
+    G: 2), no slot holds two entries, a slot's lane and step are those of the chain that reads it, and the slot tables
+    the kernel places a QP's values by (vdst, gslot in the generated source) say the same."""
+    pat = dogbot.generate(kind, 1).pattern
+    plan = qps.Plan(pat)
+    st = W.Structure(plan, True, 24)  # (with a few factor-order rows behind the value row)
+    W.gen_factor(st)
+    nP, nA, nG = len(pat.Pir), len(pat.Air), len(pat.Gir)
+    assert [len(v) for v in st.vslots] == [1] * nP + [2] * (nA + nG)
+    flat = [s for v in st.value_slots() for s in v]
+    assert len(flat) == len(set(flat)) and max(flat) < st.lay["total"] - st.lay["V"]
+    # the chain that reads slot 32 T + lane is lane's term at step T
+    T = 0
+    for grp in st.resid_groups:
+        for t in range(max(len(tl) for tl in grp)):
+            for lane, tl in enumerate(grp):
+                if t < len(tl):
+                    assert 32 * T + lane in st.vslots[tl[t][0]]
+            T += 1
+    assert 32 * T == st.lay["vzero"] - st.lay["V"]
+    # factor-order rows: 24 rows of 32 behind the zero that follows the value row
+    assert len(st.frows) == 24 and st.F0 == st.lay["vzero"] + 2 and st.lay["total"] == st.F0 + 32 * 24
+    # the generated source carries the same tables
+    import re
+    src, stats = W.generate(kind)
+    st2 = W.Structure(plan, True, 0, st.lay["pbsize"] if stats["layout"]["tsize"] == st.lay["tsize"] else 42)
+    vdst = [int(v) for v in re.search(r"unsigned short vdst\[\] = \{([^}]*)\}", src).group(1).split(",")]
+    slots = st2.value_slots()
+    k = max(len(v) for v in slots)
+    assert vdst == [v[c] if c < len(v) else 0xffff for c in range(k) for v in slots] and f"kVDst = {k};" in src
+    gslot = [int(v) for v in re.search(r"unsigned short gslot\[\] = \{([^}]*)\}", src).group(1).split(",")]
+    rows = [[] for _ in range(pat.m)]
+    for col in range(pat.n):
+        for q in range(int(pat.Gjc[col]), int(pat.Gjc[col + 1])):
+            rows[int(pat.Gir[q])].append(slots[nP + nA + q][0])
+    assert gslot == [v for r in rows for v in r] and stats["layout"]["value_row_doubles"] == st2.lay["total"] - st2.lay["smem"]
