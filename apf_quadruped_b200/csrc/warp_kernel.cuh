@@ -1,6 +1,8 @@
 // Warp-per-QP kernel of the batched interior-point solver (sm_100a, FP64): ONE WARP PER QP, the QP's whole
 // working set -- value row, factor L, pivots, iterate, residuals (SliceLayout, program.h) -- resident in the
-// warp's slice of SHARED memory from the coalesced load of its value row to the store of its solution.
+// warp's slice of SHARED memory from the coalesced load of its value row to the store of its solution (generated
+// programs keep the value row itself in a per-warp scratch row in global memory / L2, in the order the residual
+// products read it: see value_row_global, value_row_resid_order below).
 //
 // Launch shape: one persistent CTA per SM, as many warps as slices fit.  The warps of a CTA walk the
 // interior-point iteration in lock step -- [residuals + stop test | factor | solve | step length, sigma |
@@ -29,7 +31,7 @@ struct ProgramView
 
 enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_PRED = 2, MODE_CENT = 3 };
 static const int MAX_WARPS_PER_CTA = 16; // interpreted schedules: 128 registers per thread
-static const int GEN_WARPS_MAX = 16;     // generated programs: as many warps per CTA as their slices fit (trot 12, crawl 10, stance 9)
+static const int GEN_WARPS_MAX = 16;     // generated programs: as many warps per CTA as their slices fit (trot 12, crawl 11, stance 10)
 
 struct GeneratedWarpKernel
 {
