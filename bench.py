@@ -582,8 +582,9 @@ def main():
         traffic, traffic_src = ncu_traffic(f"{args.kind}:{B}:{leg.solver.last_kernel}")
         roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_solve": total_bytes / B, "traffic_gbs": traffic / (ms_step * 1e-3) / 1e9 if traffic else None, "traffic_source": traffic_src,
-                "note": ("one QP per warp, the QP's whole working set (value row, factor L, iterate) resident in shared memory from load to store: 'achieved' counts SURVEY 8d's "
-                         "algorithmic bytes (factor written once and read once per solve) although those bytes never reach HBM here -- 'traffic' (value rows in, solutions out) is what does"
+                "note": ("one QP per warp, the QP's working set resident on chip from load to store (factor L and iterate in shared memory, value row in an L2-resident scratch "
+                         "row): 'achieved' counts SURVEY 8d's algorithmic bytes (factor written once and read once per solve) although those bytes never reach HBM here -- 'traffic' "
+                         "(value rows in, solutions out, scratch rows that L2 evicted) is what does"
                          if leg.solver.last_kernel == "warp" else
                          "one QP per thread, working sets interleaved in HBM: 'achieved' = SURVEY 8d algorithmic bytes / launch time; the up-looking factorisation re-reads L row by row, "
                          "which is the gap between 'traffic' and the algorithmic bytes")}
