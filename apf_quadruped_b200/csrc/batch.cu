@@ -283,9 +283,9 @@ static int batch_alloc(QPBatch *B)
 		B->stream_slots = std::min(full, (B->capacity + 31) / 32);
 		// Which kernel takes a batch.  Without a pattern-specialised warp-per-QP kernel: the throughput kernel from
 		// 2048 QPs on.  With one (DogBot trot / stance / crawl): the warp-per-QP kernel keeps the factor in shared
-		// memory, has no tail (1,480 QPs in flight instead of 37,888) and no stragglers' hand-over, and since round 2
-		// (value row outside the slice: 10 warps per SM) it is the faster one at every batch size measured
-		// (trot 65,536: 1.70 M against 1.40 M solves/s; 262,144: 1.71 M against 1.63 M).  QPB_STREAM_MIN overrides.
+		// memory, has no tail (1,480-1,776 QPs in flight instead of 37,888) and no stragglers' hand-over, and since round 2
+		// (value row outside the slice: 10-12 warps per SM) it is the faster one at every batch size measured
+		// (trot 65,536: 2.05 M against 1.40 M solves/s; 262,144, at 10 warps: 1.71 M against 1.63 M).  QPB_STREAM_MIN overrides.
 		B->stream_min = getenv("QPB_STREAM_MIN") ? atol(getenv("QPB_STREAM_MIN")) : (B->gen_warp ? LONG_MAX : 2048);
 		// A pattern whose window leaves room for fewer than 4 warps per SM (e.g. the horizon-10 MPC QP:
 		// N = 600, one warp) is faster on the latency kernel; QPB_STREAM_MIN_WARPS overrides.
